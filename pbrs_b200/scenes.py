@@ -1,0 +1,335 @@
+"""Synthetic, seeded scene generators for the five BASELINE.json configs.
+
+The reference ships no assets (`assets/` is git-ignored) and its presets draw from an OS-seeded
+RNG (scene/src/preset.rs:18-20), so the workloads are generated here, deterministically, in the
+vocabulary of scene/src/preset.rs and scene/src/loader.rs.  Every generator takes size knobs so
+the parity tests can use small instances of the same family.
+"""
+import numpy as np
+
+from . import _capi as K
+from .scene import SceneDesc
+
+SEED = 0x5EED
+
+# metal IORs, scene/src/preset.rs:467-493
+GOLD = ((0.143176, 0.373096, 1.443834), (3.982675, 2.387439, 1.602465))
+SILVER = ((0.155184, 0.116681, 0.138360), (4.828131, 3.122411, 2.147082))
+COPPER = ((0.195470, 0.925682, 1.102186), (3.910869, 2.451263, 2.142653))
+ALUMINIUM = ((1.656937, 0.880173, 0.521201), (9.224230, 6.269670, 4.836996))
+
+
+def translate(t):
+    m = np.eye(4)
+    m[:3, 3] = t
+    return m
+
+
+def rotate_y(deg):
+    # AffineTransform::rotater(Y, angle), math/src/hcm.rs:508-520: X -> (cos, 0, sin), Z -> (-sin, 0, cos)
+    a = np.deg2rad(deg)
+    c, s = np.cos(a), np.sin(a)
+    m = np.eye(4)
+    m[:3, 0] = (c, 0, s)
+    m[:3, 2] = (-s, 0, c)
+    return m
+
+
+def rotate_axis(axis, rad):
+    axis = np.asarray(axis, np.float64)
+    axis = axis / np.linalg.norm(axis)
+    x, y, z = axis
+    c, s = np.cos(rad), np.sin(rad)
+    Kx = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+    R = np.eye(3) * c + s * Kx + (1 - c) * np.outer(axis, axis)
+    m = np.eye(4)
+    m[:3, :3] = R
+    return m
+
+
+def scale(s):
+    m = np.eye(4)
+    m[0, 0] = m[1, 1] = m[2, 2] = s
+    return m
+
+
+def _quad(p00, p10, p11, p01):
+    """Two triangles over a quad; returns (P[4,3], idx[2,3])."""
+    return np.array([p00, p10, p11, p01], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+
+
+def _box(lo, hi):
+    """Axis-aligned box as 12 triangles, outward winding not required (normals face the ray)."""
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    P = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0],
+                  [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], np.float32)
+    q = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (3, 2, 6, 7), (0, 3, 7, 4), (1, 2, 6, 5)]
+    idx = []
+    for a, b, c, d in q:
+        idx += [[a, b, c], [a, c, d]]
+    return P, np.array(idx, np.uint32)
+
+
+def cornell_box(width=512, height=512):
+    """C1/C2: Cornell box, 34 triangles (5 walls x 2 + 2 boxes x 12) + a sphere area light.
+
+    Colours from scene/src/preset.rs:196-199; camera from :249-254; the light is a sphere because
+    the loader's area lights accept only sphere/plymesh (scene/src/loader.rs:396-434, Q16); it is
+    built as the loader does (:176-195): Sphere at the origin under a Translate CTM, DiffuseLight
+    instance + DiffuseAreaLight over the transformed shape.
+    """
+    sd = SceneDesc()
+    sd.set_camera(width, height, 40.0, (278.0, 278.0, -800.0), (278.0, 278.0, 0.0), (0, 1, 0))
+    red = sd.lambertian((0.65, 0.05, 0.05))
+    white = sd.lambertian((0.73, 0.73, 0.73))
+    green = sd.lambertian((0.12, 0.45, 0.15))
+    L = (15.0, 15.0, 15.0)
+    light = sd.diffuse_light(L)
+    S = 555.0
+    walls = [
+        (_quad((S, 0, 0), (S, S, 0), (S, S, S), (S, 0, S)), green),      # x = 555
+        (_quad((0, 0, 0), (0, S, 0), (0, S, S), (0, 0, S)), red),        # x = 0
+        (_quad((0, 0, 0), (S, 0, 0), (S, 0, S), (0, 0, S)), white),      # floor
+        (_quad((0, S, 0), (S, S, 0), (S, S, S), (0, S, S)), white),      # ceiling
+        (_quad((0, 0, S), (S, 0, S), (S, S, S), (0, S, S)), white),      # back
+    ]
+    for (P, idx), m in walls:
+        sd.add_instance(sd.add_mesh(P, idx), m)
+    P, idx = _box((0, 0, 0), (165, 165, 165))
+    sd.add_instance(sd.add_mesh(P, idx), white, fwd=translate((265, 0, 105)) @ rotate_y(15.0))
+    P, idx = _box((0, 0, 0), (165, 330, 165))
+    sd.add_instance(sd.add_mesh(P, idx), white, fwd=translate((130, 0, 225)) @ rotate_y(-18.0))
+    c, r = (278.0, 514.0, 279.5), 40.0
+    sd.add_instance(sd.add_sphere((0, 0, 0), r), light, fwd=translate(c))
+    sd.add_area_light_sphere(c, r, L)
+    return sd
+
+
+def spheres500(width=1920, height=1080, n_small=496, seed=SEED):
+    """C3: ground + 3 big + n_small small spheres, Lambertian/Metal/Dielectric, blue-sky env.
+
+    In the style of preset::mixed_spheres (scene/src/preset.rs:55-113): each sphere is its own
+    TLAS instance with the identity transform.
+    """
+    rng = np.random.default_rng(seed)
+    sd = SceneDesc()
+    sd.set_camera(width, height, 25.0, (13.0, 2.0, 3.0), (0.0, 0.0, 0.0), (0, 1, 0))
+    sd.add_instance(sd.add_sphere((0.0, -1000.0, 1.0), 1000.0), sd.lambertian((0.5, 0.5, 0.5)))
+    sd.add_instance(sd.add_sphere((0.0, 1.0, 0.0), 1.0), sd.dielectric(1.5))
+    sd.add_instance(sd.add_sphere((-4.0, 1.0, 0.0), 1.0), sd.lambertian((0.4, 0.2, 0.1)))
+    sd.add_instance(sd.add_sphere((4.0, 1.0, 0.0), 1.0), sd.metal(GOLD[0], GOLD[1], 0.0))
+    metals = [GOLD, SILVER, COPPER, ALUMINIUM]
+    count = 0
+    cells = [(a, b) for a in range(-12, 12) for b in range(-11, 10)]
+    for a, b in cells:
+        if count >= n_small:
+            break
+        choose = rng.random()
+        center = np.array([a + 0.9 * rng.random(), 0.2 + 0.1 * rng.random() ** 3, b + 0.9 * rng.random()])
+        if np.linalg.norm(center - np.array([4.0, 0.2, 0.0])) <= 0.9:
+            continue
+        if choose < 0.8:
+            m = sd.lambertian(tuple(rng.random(3)))
+        elif choose < 0.95:
+            eta, k = metals[int(rng.integers(0, 4))]
+            m = sd.metal(eta, k, float(rng.random() * 0.5))
+        else:
+            m = sd.dielectric(1.4)
+        sd.add_instance(sd.add_sphere(tuple(center), 0.2), m)
+        count += 1
+    sd.set_env_fn(K.ENV_BLUE_SKY)
+    return sd
+
+
+def _value_noise(x, y, seed, octaves=4):
+    """Seeded 2-D value noise, sum of octaves; x, y float arrays."""
+    rng = np.random.default_rng(seed)
+    tab = rng.random((256, 256))
+    out = np.zeros_like(x, dtype=np.float64)
+    amp, freq = 1.0, 1.0
+    for _ in range(octaves):
+        xf, yf = x * freq, y * freq
+        x0, y0 = np.floor(xf).astype(int), np.floor(yf).astype(int)
+        tx, ty = xf - x0, yf - y0
+        tx, ty = tx * tx * (3 - 2 * tx), ty * ty * (3 - 2 * ty)
+        v00 = tab[x0 & 255, y0 & 255]; v10 = tab[(x0 + 1) & 255, y0 & 255]
+        v01 = tab[x0 & 255, (y0 + 1) & 255]; v11 = tab[(x0 + 1) & 255, (y0 + 1) & 255]
+        out += amp * ((v00 * (1 - tx) + v10 * tx) * (1 - ty) + (v01 * (1 - tx) + v11 * tx) * ty)
+        amp *= 0.5
+        freq *= 2.0
+    return out
+
+
+def compute_normals(P, idx):
+    """geometry/src/lib.rs:16-32: area-weighted face normals summed per vertex, normalised."""
+    P64 = P.astype(np.float64)
+    n = np.cross(P64[idx[:, 1]] - P64[idx[:, 0]], P64[idx[:, 2]] - P64[idx[:, 0]])
+    N = np.zeros_like(P64)
+    for k in range(3):
+        np.add.at(N, idx[:, k], n)
+    N /= np.maximum(np.linalg.norm(N, axis=1, keepdims=True), 1e-30)
+    return N.astype(np.float32)
+
+
+def heightfield(grid, extent=40.0, height=3.0, seed=SEED):
+    """(grid x grid quads) displaced height-field: P, N, UV, idx (2*grid^2 triangles)."""
+    g = np.linspace(0.0, 1.0, grid + 1)
+    U, V = np.meshgrid(g, g, indexing="ij")
+    X = (U - 0.5) * extent
+    Z = (V - 0.5) * extent
+    Y = height * (_value_noise(U * 6.0, V * 6.0, seed) - 0.9)
+    P = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    UV = np.stack([U, V], -1).reshape(-1, 2).astype(np.float32)
+    i, j = np.meshgrid(np.arange(grid), np.arange(grid), indexing="ij")
+    v00 = (i * (grid + 1) + j).reshape(-1)
+    v10 = v00 + (grid + 1)
+    v01 = v00 + 1
+    v11 = v10 + 1
+    idx = np.concatenate([np.stack([v00, v01, v11], -1), np.stack([v00, v11, v10], -1)], 0).astype(np.uint32)
+    # interleave the two triangles of each quad so that spatially close triangles are close in memory
+    idx = idx.reshape(2, -1, 3).transpose(1, 0, 2).reshape(-1, 3)
+    N = compute_normals(P, idx)
+    # height-field normals must point up (+Y)
+    N[N[:, 1] < 0] *= -1
+    return P, N, UV, np.ascontiguousarray(idx)
+
+
+def icosphere(subdiv, radius=1.0, bump=0.0, seed=0):
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    V = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    F = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5],
+                  [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], np.int64)
+    for _ in range(subdiv):
+        edges = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]], 0)
+        edges.sort(axis=1)
+        uniq, inv = np.unique(edges, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        mid = V[uniq[:, 0]] + V[uniq[:, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        base = V.shape[0]
+        V = np.concatenate([V, mid], 0)
+        nf = F.shape[0]
+        a, b, c = base + inv[:nf], base + inv[nf:2 * nf], base + inv[2 * nf:]
+        F = np.concatenate([np.stack([F[:, 0], a, c], -1), np.stack([F[:, 1], b, a], -1),
+                            np.stack([F[:, 2], c, b], -1), np.stack([a, b, c], -1)], 0)
+    N = V.copy()
+    if bump > 0.0:
+        rng = np.random.default_rng(seed)
+        k = rng.normal(size=(4, 3)) * 2.0
+        ph = rng.random(4) * 6.28
+        d = sum(np.sin(V @ k[i] + ph[i]) for i in range(4)) / 4.0
+        V = V * (1.0 + bump * d)[:, None]
+    P = (V * radius).astype(np.float32)
+    theta = np.arccos(np.clip(N[:, 1], -1, 1)) / np.pi
+    phi = (np.arctan2(N[:, 2], N[:, 0]) + np.pi) / (2 * np.pi)
+    UV = np.stack([phi, theta], -1).astype(np.float32)
+    idx = F.astype(np.uint32)
+    Nn = compute_normals(P, idx) if bump > 0.0 else N.astype(np.float32)
+    # make normals outward
+    flip = np.sum(Nn * N, axis=1) < 0
+    Nn[flip] *= -1
+    return P, Nn, UV, idx
+
+
+def checker_noise_image(size=1024, seed=SEED):
+    g = np.arange(size)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    chk = ((X // (size // 16)) + (Y // (size // 16))) % 2
+    n = _value_noise(X / 37.0, Y / 37.0, seed + 1)
+    n = (n - n.min()) / (n.max() - n.min())
+    base = np.where(chk[..., None] == 1, np.array([0.75, 0.62, 0.38]), np.array([0.28, 0.45, 0.22]))
+    img = np.clip(base * (0.6 + 0.4 * n[..., None]), 0, 1)
+    return (img * 255).astype(np.uint8)
+
+
+def mesh_terrain(width=3840, height=2160, grid=708, ico_subdiv=5, tex_size=1024, seed=SEED):
+    """C4: one TriangleMesh of 2*grid^2 triangles (708 -> 1,002,528) with an image-textured
+    Lambertian, 8 floating icospheres (20*4^subdiv triangles each) in Plastic/Glossy, one sphere
+    area light and a constant env of 0.1."""
+    rng = np.random.default_rng(seed)
+    sd = SceneDesc()
+    sd.set_camera(width, height, 40.0, (0.0, 9.0, -30.0), (0.0, -1.0, 0.0), (0, 1, 0))
+    P, N, UV, idx = heightfield(grid, seed=seed)
+    tex = sd.add_texture_image(checker_noise_image(tex_size, seed))
+    sd.add_instance(sd.add_mesh(P, idx, N=N, UV=UV), sd.lambertian(tex=tex))
+    Pi, Ni, UVi, idxi = icosphere(ico_subdiv)
+    ico = sd.add_mesh(Pi, idxi, N=Ni, UV=UVi)
+    for k in range(8):
+        pos = (float(rng.uniform(-14, 14)), float(rng.uniform(1.0, 5.0)), float(rng.uniform(-12, 12)))
+        s = float(rng.uniform(0.8, 1.8))
+        if k % 2 == 0:
+            m = sd.plastic(tuple(rng.uniform(0.2, 0.8, 3)), (0.3, 0.3, 0.3), float(rng.uniform(0.05, 0.3)))
+        else:
+            m = sd.glossy(tuple(rng.uniform(0.5, 0.95, 3)), float(rng.uniform(0.01, 0.2)))
+        sd.add_instance(ico, m, fwd=translate(pos) @ rotate_y(float(rng.uniform(0, 360))) @ scale(s))
+    c, r, L = (6.0, 16.0, -6.0), 2.5, (40.0, 38.0, 34.0)
+    sd.add_instance(sd.add_sphere((0, 0, 0), r), sd.diffuse_light(L), fwd=translate(c))
+    sd.add_area_light_sphere(c, r, L)
+    sd.set_env_constant((0.1, 0.1, 0.1))
+    return sd
+
+
+def instanced_field(width=3840, height=2160, n_side=100, n_meshes=10, ico_subdiv=3, n_lights=16, seed=SEED):
+    """C5: n_side^2 instances (random rotation + uniform scale on a jittered grid) of n_meshes
+    distinct bumpy icospheres (20*4^3 = 1280 triangles each; 10k instances ~ 12.8 M instanced
+    triangles), a ground quad, n_lights sphere area lights, mixed materials."""
+    rng = np.random.default_rng(seed)
+    sd = SceneDesc()
+    ext = float(n_side) * 2.5
+    sd.set_camera(width, height, 40.0, (0.0, ext * 0.22, -ext * 0.62), (0.0, 0.0, -ext * 0.05), (0, 1, 0))
+    Pg, ig = _quad((-ext, 0, -ext), (ext, 0, -ext), (ext, 0, ext), (-ext, 0, ext))
+    sd.add_instance(sd.add_mesh(Pg, ig), sd.lambertian((0.45, 0.45, 0.42)))
+    meshes = []
+    for k in range(n_meshes):
+        P, N, UV, idx = icosphere(ico_subdiv, bump=0.25, seed=seed + 100 + k)
+        meshes.append(sd.add_mesh(P, idx, N=N, UV=UV))
+    mats = []
+    for k in range(24):
+        c = rng.random()
+        if c < 0.6:
+            mats.append(sd.lambertian(tuple(rng.uniform(0.15, 0.9, 3))))
+        elif c < 0.75:
+            eta, kk = [GOLD, SILVER, COPPER, ALUMINIUM][int(rng.integers(0, 4))]
+            mats.append(sd.metal(eta, kk, float(rng.uniform(0.02, 0.4))))
+        elif c < 0.9:
+            mats.append(sd.plastic(tuple(rng.uniform(0.2, 0.8, 3)), (0.25, 0.25, 0.25), float(rng.uniform(0.05, 0.3))))
+        else:
+            mats.append(sd.mirror((0.9, 0.9, 0.9)))
+    cell = 2.0 * ext / n_side
+    for i in range(n_side):
+        for j in range(n_side):
+            x = -ext + (i + 0.5 + rng.uniform(-0.3, 0.3)) * cell
+            z = -ext + (j + 0.5 + rng.uniform(-0.3, 0.3)) * cell
+            s = float(rng.uniform(0.6, 1.2)) * cell * 0.35
+            axis = rng.normal(size=3)
+            fwd = translate((x, s * 1.05, z)) @ rotate_axis(axis, float(rng.uniform(0, 6.28))) @ scale(s)
+            sd.add_instance(meshes[int(rng.integers(0, n_meshes))], mats[int(rng.integers(0, len(mats)))], fwd=fwd)
+    for k in range(n_lights):
+        c = (float(rng.uniform(-ext * 0.8, ext * 0.8)), float(rng.uniform(ext * 0.12, ext * 0.3)),
+             float(rng.uniform(-ext * 0.8, ext * 0.8)))
+        r = float(rng.uniform(1.0, 2.5)) * max(1.0, n_side / 40.0)
+        L = tuple(float(v) for v in rng.uniform(20.0, 60.0, 3))
+        sd.add_instance(sd.add_sphere((0, 0, 0), r), sd.diffuse_light(L), fwd=translate(c))
+        sd.add_area_light_sphere(c, r, L)
+    return sd
+
+
+# name -> (generator, integrator, msaa) : the BASELINE.json configs
+CONFIGS = {
+    "c1": (lambda: cornell_box(512, 512), "path", 4),
+    "c2": (lambda: cornell_box(1920, 1080), "direct", 1),
+    "c3": (lambda: spheres500(1920, 1080), "path", 8),
+    "c4": (lambda: mesh_terrain(3840, 2160), "path", 16),
+    "c5": (lambda: instanced_field(3840, 2160), "path", 32),
+}
+WORKLOAD_NAMES = {
+    "c1": "C1 cornell-box 512x512 16spp path depth5",
+    "c2": "C2 cornell-box 1920x1080 1spp direct",
+    "c3": "C3 500-spheres 1920x1080 64spp path depth5",
+    "c4": "C4 1M-triangle terrain 3840x2160 256spp path depth5",
+    "c5": "C5 10k-instance field (~12.8M tris) 3840x2160 1024spp path depth5",
+}

@@ -199,6 +199,7 @@ typedef struct pbrs_stats {
 #define PBRS_PANIC_PERLIN 9        /* noise range asserts (texture/src/lib.rs:134-135)       */
 #define PBRS_PANIC_REFRACT 10      /* assert_ge!(cos_theta_i, 0) (hcm.rs:629)                */
 #define PBRS_PANIC_MISC 11
+#define PBRS_PANIC_STACK 12         /* not a reference assert: a traversal stack overflowed    */
 
 /* Renders this rank's share of the frame and returns the film in HOST memory:
  * out_rgb is width*height*3 floats, row-major, row 0 = top (src/main.rs:219-231), already

@@ -1,0 +1,380 @@
+// sm_100a kernels of the wavefront and the host loop that enqueues them.
+//
+// Every kernel is persistent: the grid is sized once to fill the 148 SMs (occupancy x SM count)
+// and each warp strides over its queue in 32-path groups, reading the queue length from HBM, so
+// the host never synchronises between stages -- a whole frame is one stream of launches.
+// Queue appends are compacted per warp: one ballot, one atomicAdd by the leader, a popc prefix.
+// Tensor cores are unused on purpose: there is no dense contraction anywhere on this path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "device_stages.cuh"
+#include "render.h"
+
+namespace pbrs {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// one atomic per warp; returns this lane's slot (valid only where pred)
+__device__ __forceinline__ uint32_t warp_push(uint32_t *count, bool pred) {
+    unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (m == 0u) return 0u;
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0u;
+    if ((int)lane_id() == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane_id()) - 1u));
+}
+__device__ __forceinline__ void warp_add_stat(unsigned long long *dst, uint32_t v) {
+    uint32_t s = __reduce_add_sync(0xFFFFFFFFu, v);
+    if (lane_id() == 0u && s != 0u) atomicAdd(dst, (unsigned long long)s);
+}
+__device__ __forceinline__ void flush_diag(unsigned long long *stats, const Diag &dg) {
+    uint32_t any = __reduce_or_sync(0xFFFFFFFFu, dg.panics);
+    if (any == 0u) return;
+    for (int k = 0; k < 16; ++k)
+        if (any & (1u << k)) {
+            uint32_t c = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, (dg.panics >> k) & 1u));
+            if (lane_id() == 0u) atomicAdd(stats + kStatPanic0 + k, (unsigned long long)c);
+        }
+}
+__device__ __forceinline__ void flush_count(unsigned long long *stats, const TravCount &tc) {
+    warp_add_stat(stats + kStatNodes, tc.nodes);
+    warp_add_stat(stats + kStatTris, tc.tris);
+    warp_add_stat(stats + kStatSpheres, tc.spheres);
+    warp_add_stat(stats + kStatInsts, tc.insts);
+}
+
+// warp-uniform strided loop over [0, n): `body(idx, active)` runs with all 32 lanes converged
+#define PBRS_WARP_LOOP(n_expr, idx, active)                                                           \
+    const uint32_t _n = (n_expr);                                                                     \
+    const uint32_t _warps = (gridDim.x * blockDim.x) >> 5;                                            \
+    for (uint32_t _b = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; _b < _n; _b += _warps * 32u) \
+        if (uint32_t idx = _b + lane_id(); true)                                                      \
+            if (bool active = idx < _n; true)
+
+__global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *out_count) {
+    PBRS_WARP_LOOP(bp.n_paths, j, active) {
+        bool live = active && stage_generate(sc, pb, fp, bp, j);
+        uint32_t slot = warp_push(out_count, live);
+        if (live) pb.queue[0][slot] = j;
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_extend(DeviceScene sc, PathBuffers pb, const uint32_t *queue, const uint32_t *count) {
+    Diag dg; dg.panics = 0u;
+    TravCount tc; tc.nodes = tc.tris = tc.spheres = tc.insts = 0u;
+    PBRS_WARP_LOOP(*count, i, active) {
+        if (active) stage_extend<COUNT>(sc, pb, queue[i], dg, tc);
+    }
+    __syncwarp();
+    flush_diag(pb.stats, dg);
+    if (COUNT) flush_count(pb.stats, tc);
+}
+
+__global__ void __launch_bounds__(kThreads) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, const uint32_t *queue,
+                                                    const uint32_t *count, uint32_t *next_queue, uint32_t *next_count, uint32_t *shadow_count,
+                                                    int bounce) {
+    Diag dg; dg.panics = 0u;
+    uint32_t rays = 0u;
+    PBRS_WARP_LOOP(*count, i, active) {
+        ShadeOut so; so.next = false; so.shadow_rays = 0;
+        uint32_t j = 0u;
+        if (active) {
+            j = queue[i];
+            so = fp.integrator == PBRS_INTEGRATOR_PATH ? stage_shade_path(sc, pb, fp, bp, j, bounce, dg)
+                                                       : stage_shade_direct(sc, pb, fp, bp, j, bounce, dg);
+        }
+        uint32_t s1 = warp_push(next_count, so.next);
+        if (so.next) next_queue[s1] = j;
+        uint32_t s2 = warp_push(shadow_count, so.shadow_rays > 0);
+        if (so.shadow_rays > 0) pb.shadow_queue[s2] = j;
+        rays += (uint32_t)so.shadow_rays;
+    }
+    __syncwarp();
+    warp_add_stat(pb.stats + kStatShadowRays, rays);
+    flush_diag(pb.stats, dg);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_shadow(DeviceScene sc, PathBuffers pb, const uint32_t *count) {
+    Diag dg; dg.panics = 0u;
+    TravCount tc; tc.nodes = tc.tris = tc.spheres = tc.insts = 0u;
+    PBRS_WARP_LOOP(*count, i, active) {
+        if (active) stage_shadow<COUNT>(sc, pb, pb.shadow_queue[i], dg, tc);
+    }
+    __syncwarp();
+    flush_diag(pb.stats, dg);
+    if (COUNT) flush_count(pb.stats, tc);
+}
+
+__global__ void __launch_bounds__(kThreads) k_accumulate(PathBuffers pb, FrameParams fp, BatchParams bp, float *film) {
+    PBRS_WARP_LOOP(bp.n_pixels, p, active) {
+        if (active) stage_accumulate(pb, fp, bp, p, film);
+    }
+}
+
+// parity side channels ------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_write_ids(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *out_inst,
+                                                        uint32_t *out_prim, float *out_t) {
+    PBRS_WARP_LOOP(bp.n_paths, j, active) {
+        if (!active) continue;
+        PathId id = decode_path(fp, bp, j);
+        if (!id.valid) continue;
+        uint4 h = *reinterpret_cast<const uint4 *>(pb.hit + j);
+        size_t k = (size_t)(id.y - fp.y0) * (fp.x1 - fp.x0) + (id.x - fp.x0);
+        bool hit = h.y != 0xFFFFFFFFu;
+        uint32_t prim = 0xFFFFFFFFu;
+        if (hit) {
+            uint32_t kind = sc.inst_trav[h.y].shape_kind;
+            prim = kind == PBRS_SHAPE_MESH ? sc.tris[h.z].orig : 0u;
+        }
+        if (out_inst) out_inst[k] = hit ? h.y : 0xFFFFFFFFu;
+        if (out_prim) out_prim[k] = prim;
+        if (out_t) out_t[k] = hit ? __uint_as_float(h.x) : PB_INF;
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_write_samples(PathBuffers pb, FrameParams fp, BatchParams bp, float *out) {
+    PBRS_WARP_LOOP(bp.n_paths, j, active) {
+        if (!active) continue;
+        PathId id = decode_path(fp, bp, j);
+        if (!id.valid) continue;
+        float4 r = *reinterpret_cast<const float4 *>(pb.rad + j);
+        size_t k = ((size_t)(id.y - fp.y0) * (fp.x1 - fp.x0) + (id.x - fp.x0)) * fp.spp + id.sample;
+        out[3 * k] = r.x; out[3 * k + 1] = r.y; out[3 * k + 2] = r.z;
+    }
+}
+
+struct Grid {
+    int extend, extend_count, shade, shadow, shadow_count, small;
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                              \
+            return PBRS_ERR_CUDA;                                                                       \
+        }                                                                                               \
+    } while (0)
+
+template <class K>
+int blocks_for(K kernel, int sms) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+}  // namespace
+
+struct Workspace {
+    int device = -1;
+    uint32_t capacity = 0;
+    char *slab = nullptr;
+    size_t slab_bytes = 0;
+    PathBuffers pb{};
+    uint32_t *counts = nullptr;
+    uint32_t counts_cap = 0;   // in batches
+    uint32_t *tiles = nullptr;
+    uint32_t tiles_cap = 0;
+    unsigned long long *stats = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int sms = 0;
+    Grid grid{};
+    bool grid_ready = false;
+};
+
+void workspace_free(Workspace *w) {
+    if (!w) return;
+    if (w->slab) cudaFree(w->slab);
+    if (w->counts) cudaFree(w->counts);
+    if (w->tiles) cudaFree(w->tiles);
+    if (w->stats) cudaFree(w->stats);
+    for (auto &e : w->ev) if (e) cudaEventDestroy(e);
+    delete w;
+}
+
+static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint32_t n_batches, uint32_t n_tiles) {
+    if (!wp) wp = new Workspace();
+    Workspace &w = *wp;
+    if (w.device != device) {
+        w.device = device;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        w.sms = prop.multiProcessorCount;
+    }
+    if (!w.grid_ready) {
+        w.grid.extend = blocks_for(k_extend<false>, w.sms);
+        w.grid.extend_count = blocks_for(k_extend<true>, w.sms);
+        w.grid.shade = blocks_for(k_shade, w.sms);
+        w.grid.shadow = blocks_for(k_shadow<false>, w.sms);
+        w.grid.shadow_count = blocks_for(k_shadow<true>, w.sms);
+        w.grid.small = blocks_for(k_generate, w.sms);
+        w.grid_ready = true;
+    }
+    if (!w.ev[0]) { CK(cudaEventCreate(&w.ev[0])); CK(cudaEventCreate(&w.ev[1])); }
+    if (!w.stats) CK(cudaMalloc(&w.stats, sizeof(unsigned long long) * kStatCount));
+    if (w.capacity < capacity) {
+        if (w.slab) { cudaFree(w.slab); w.slab = nullptr; }
+        // 13 x 16-byte arrays + 1 float + 3 queues per path slot
+        size_t per = 13 * sizeof(f4) + sizeof(float) + 3 * sizeof(uint32_t);
+        size_t bytes = per * (size_t)capacity + 4096;
+        cudaError_t e = cudaMalloc(&w.slab, bytes);
+        if (e != cudaSuccess) { set_error("path workspace: out of device memory"); w.capacity = 0; return PBRS_ERR_OOM; }
+        w.slab_bytes = bytes;
+        w.capacity = capacity;
+        char *p = w.slab;
+        auto take = [&](size_t elem) { char *q = p; p += elem * (size_t)capacity; return q; };
+        PathBuffers &pb = w.pb;
+        pb.ray_o = (f4 *)take(16); pb.ray_d = (f4 *)take(16); pb.hit = (u4 *)take(16); pb.beta = (f4 *)take(16);
+        pb.rad = (f4 *)take(16); pb.aux = (f4 *)take(16);
+        pb.sh_o1 = (f4 *)take(16); pb.sh_d1 = (f4 *)take(16); pb.sh_o2 = (f4 *)take(16); pb.sh_d2 = (f4 *)take(16);
+        pb.sh_c = (f4 *)take(16); pb.sh_b = (f4 *)take(16);
+        (void)take(16);  // spare
+        pb.sh_m = (float *)take(4);
+        pb.queue[0] = (uint32_t *)take(4); pb.queue[1] = (uint32_t *)take(4); pb.shadow_queue = (uint32_t *)take(4);
+        pb.capacity = capacity;
+    }
+    if (w.counts_cap < n_batches) {
+        if (w.counts) cudaFree(w.counts);
+        CK(cudaMalloc(&w.counts, sizeof(uint32_t) * PBRS_COUNTS_PER_BATCH * (size_t)n_batches));
+        w.counts_cap = n_batches;
+    }
+    if (w.tiles_cap < n_tiles) {
+        if (w.tiles) cudaFree(w.tiles);
+        CK(cudaMalloc(&w.tiles, sizeof(uint32_t) * (size_t)n_tiles));
+        w.tiles_cap = n_tiles;
+    }
+    w.pb.stats = w.stats;
+    return 0;
+}
+
+int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st) {
+    if (!s.committed) { set_error("render before pbrs_scene_commit"); return PBRS_ERR_STATE; }
+    if (o.msaa == 0) { set_error("msaa must be >= 1"); return PBRS_ERR_INVALID_ARG; }
+    if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) { set_error("bad rank/world_size"); return PBRS_ERR_INVALID_ARG; }
+    if (o.integrator != PBRS_INTEGRATOR_PATH && o.integrator != PBRS_INTEGRATOR_DIRECT) { set_error("unknown integrator"); return PBRS_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(s.device));
+    const uint32_t W = s.cam.width, H = s.cam.height;
+    FrameParams fp{};
+    fp.seed = o.seed; fp.msaa = o.msaa; fp.spp = o.msaa * o.msaa;
+    fp.rank = (uint32_t)o.rank; fp.world = (uint32_t)o.world_size;
+    fp.split_samples = (o.world_size > 1 && o.split == PBRS_SPLIT_SAMPLES) ? 1u : 0u;
+    fp.only_sample = tg.only_sample;
+    fp.integrator = o.integrator; fp.max_depth = o.max_depth; fp.flags = o.flags;
+    fp.width = W; fp.height = H;
+    if (o.crop_w == 0 || o.crop_h == 0) { fp.x0 = 0; fp.y0 = 0; fp.x1 = W; fp.y1 = H; }
+    else {
+        if (o.crop_x + o.crop_w > W || o.crop_y + o.crop_h > H) { set_error("crop outside the frame"); return PBRS_ERR_INVALID_ARG; }
+        fp.x0 = o.crop_x; fp.y0 = o.crop_y; fp.x1 = o.crop_x + o.crop_w; fp.y1 = o.crop_y + o.crop_h;
+    }
+    if (fp.only_sample >= 0) fp.spp_r = 1;
+    else if (fp.split_samples) fp.spp_r = fp.spp > fp.rank ? (fp.spp - fp.rank + fp.world - 1) / fp.world : 0;
+    else fp.spp_r = fp.spp;
+    const bool tile_split = o.world_size > 1 && o.split == PBRS_SPLIT_TILES;
+    const uint32_t tiles_x = (W + 63) / 64;
+    std::vector<uint32_t> tiles;
+    for (uint32_t ty = fp.y0 / 64; ty <= (fp.y1 - 1) / 64; ++ty)
+        for (uint32_t tx = fp.x0 / 64; tx <= (fp.x1 - 1) / 64; ++tx) {
+            uint32_t t = ty * tiles_x + tx;
+            if (tile_split && (t % fp.world) != fp.rank) continue;
+            tiles.push_back(t);
+        }
+    fp.n_tiles = (uint32_t)tiles.size();
+
+    // stages per path: the path integrator's bounce loop, or the direct integrator's two stages
+    int n_stages = o.integrator == PBRS_INTEGRATOR_PATH ? std::max(o.max_depth, 0) : (o.max_depth > 0 ? 2 : 0);
+    if (tg.only_sample >= 0) n_stages = 1;
+    if (n_stages > PBRS_COUNTS_PER_BATCH / 2 - 1) { set_error("max_depth too large"); return PBRS_ERR_INVALID_ARG; }
+
+    uint32_t capacity = o.paths_in_flight ? o.paths_in_flight : (1u << 22);
+    const uint64_t total_pixels = (uint64_t)fp.n_tiles * 4096u;
+    const uint64_t total_paths = total_pixels * fp.spp_r;
+    if (total_paths < capacity) capacity = (uint32_t)std::max<uint64_t>(total_paths, 32);
+    if (capacity < fp.spp_r) capacity = fp.spp_r;
+    const uint32_t ppb = std::max<uint32_t>(1u, capacity / std::max(fp.spp_r, 1u));  // pixels per batch
+    const uint32_t n_batches = fp.spp_r == 0 ? 0 : (uint32_t)((total_pixels + ppb - 1) / ppb);
+
+    Workspace *&wp = s.workspace;
+    int rc = workspace_prepare(wp, s.device, capacity, std::max(n_batches, 1u), std::max(fp.n_tiles, 1u));
+    if (rc < 0) return rc;
+    Workspace &w = *wp;
+    PathBuffers pb = w.pb;
+    const bool count_trav = (o.flags & PBRS_FLAG_COUNT_TRAVERSAL) != 0;
+    const bool want_stats = st != nullptr;
+
+    if (fp.n_tiles) CK(cudaMemcpyAsync(w.tiles, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, stream));
+    fp.tiles = w.tiles;
+    CK(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * kStatCount, stream));
+    if (n_batches) CK(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * PBRS_COUNTS_PER_BATCH * (size_t)n_batches, stream));
+    if (tg.film) CK(cudaMemsetAsync(tg.film, 0, sizeof(float) * 3 * (size_t)W * H, stream));
+    if (want_stats) CK(cudaEventRecord(w.ev[0], stream));
+
+    uint64_t launches = 0, launches_extend = 0;
+    const DeviceScene &sc = s.dscene;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        BatchParams bp;
+        bp.first_pixel = b * ppb;
+        bp.n_pixels = (uint32_t)std::min<uint64_t>(ppb, total_pixels - (uint64_t)b * ppb);
+        bp.n_paths = bp.n_pixels * fp.spp_r;
+        pb.counts = w.counts + (size_t)b * PBRS_COUNTS_PER_BATCH;
+        k_generate<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, pb.counts + 0);
+        ++launches;
+        for (int stage = 0; stage < n_stages; ++stage) {
+            uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
+            uint32_t *c_in = pb.counts + 2 * stage, *c_shadow = pb.counts + 2 * stage + 1, *c_out = pb.counts + 2 * (stage + 1);
+            if (count_trav) k_extend<true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, c_in);
+            else k_extend<false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, c_in);
+            ++launches; ++launches_extend;
+            if (tg.only_sample >= 0) break;
+            k_shade<<<w.grid.shade, kThreads, 0, stream>>>(sc, pb, fp, bp, q_in, c_in, q_out, c_out, c_shadow, stage);
+            if (count_trav) k_shadow<true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, c_shadow);
+            else k_shadow<false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, c_shadow);
+            launches += 2;
+        }
+        if (tg.only_sample >= 0) {
+            k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
+            ++launches;
+        } else {
+            if (tg.film) { k_accumulate<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.film); ++launches; }
+            if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; }
+        }
+    }
+    CK(cudaGetLastError());
+    if (want_stats) {
+        CK(cudaEventRecord(w.ev[1], stream));
+        CK(cudaEventSynchronize(w.ev[1]));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]));
+        std::vector<uint32_t> counts((size_t)PBRS_COUNTS_PER_BATCH * std::max(n_batches, 1u), 0u);
+        unsigned long long stats[kStatCount];
+        if (n_batches) CK(cudaMemcpy(counts.data(), w.counts, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(stats, w.stats, sizeof stats, cudaMemcpyDeviceToHost));
+        std::memset(st, 0, sizeof *st);
+        uint64_t rays_extend = 0;
+        for (uint32_t b = 0; b < n_batches; ++b)
+            for (int stage = 0; stage < n_stages; ++stage) rays_extend += counts[(size_t)b * PBRS_COUNTS_PER_BATCH + 2 * stage];
+        st->n_samples = counts.empty() ? 0 : 0;
+        for (uint32_t b = 0; b < n_batches; ++b) st->n_samples += counts[(size_t)b * PBRS_COUNTS_PER_BATCH];
+        st->n_rays_extend = rays_extend;
+        st->n_rays_shadow = stats[kStatShadowRays];
+        st->n_nodes = stats[kStatNodes]; st->n_tris = stats[kStatTris]; st->n_spheres = stats[kStatSpheres]; st->n_instances = stats[kStatInsts];
+        for (int k = 0; k < 16; ++k) st->would_panic[k] = stats[kStatPanic0 + k];
+        st->ms_total = ms;
+        st->launches = launches;
+        st->launches_extend = launches_extend;
+        if (stats[kStatPanic0 + P_STACK]) { set_error("a traversal stack overflowed"); return PBRS_ERR_UNSUPPORTED; }
+    }
+    return 0;
+}
+
+}  // namespace pbrs

@@ -1,0 +1,173 @@
+// Flattened scene records as they sit in HBM (DESIGN.md "Data layout").  Plain POD, shared by
+// the host flattener (scene_host.cpp) and the device kernels (kernels.cu).
+//
+// Sizes are the ones SURVEY.md 8(d) prices a ray with:
+//   inner node   64 B  (both children's boxes + links: one fetch per expansion)
+//   triangle     48 B  (3 x float4 positions, ids in the pad lanes)
+//   sphere       16 B  (centre + radius)
+//   instance    128 B  (64 B traversal half: inverse 3x4 + shape link;
+//                       64 B shading half: forward 3x4 + material link)
+#pragma once
+#include <stdint.h>
+
+namespace pbrs {
+
+// Child link encoding in NodeRec::meta:
+//   bits 0..1   split axis (BLAS only; tlas/src/bvh.rs keeps no axis)
+//   bit  2      left child is a leaf      bit 3  right child is a leaf
+//   bits 4..17  left leaf primitive count  bits 18..31 right leaf primitive count (informative)
+// For a leaf child, child[k] = first primitive (BLAS: index into the mesh's triangle
+// records, relative to the mesh's first record; the leaf runs up to and including the first
+// record carrying PBRS_TRI_LAST_IN_LEAF.  TLAS: instance id).  For an inner child,
+// child[k] = node index (BLAS: relative to the mesh's first node).
+struct NodeRec {
+    float lmin[3], lmax[3];
+    float rmin[3], rmax[3];
+    uint32_t child[2];
+    uint32_t meta;
+    uint32_t pad;
+};
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
+#define PBRS_NODE_LEFT_LEAF 4u
+#define PBRS_NODE_RIGHT_LEAF 8u
+#define PBRS_MAX_LEAF_PRIMS 16383u
+
+// p0/p1/p2 already carry the reference's (i, k, j) vertex swap (shape/src/blas.rs:162-163):
+// p0 = pos[idx.0], p1 = pos[idx.2], p2 = pos[idx.1].
+struct TriRec {
+    float p0[3];
+    uint32_t orig;   // triangle index in the caller's idx array (the primitive id)
+    float p1[3];
+    uint32_t flags;  // PBRS_TRI_*
+    float p2[3];
+    uint32_t pad;
+};
+static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+// The hit can be rejected by TriangleMesh::intersect_triangle's tangent check
+// (shape/src/blas.rs:193-201); the traversal must evaluate the shading interpolation for it.
+#define PBRS_TRI_CHECK_SHADING 1u
+#define PBRS_TRI_LAST_IN_LEAF 2u
+
+struct SphereRec {
+    float c[3];
+    float r;
+};
+static_assert(sizeof(SphereRec) == 16, "SphereRec must be 16 bytes");
+
+#define PBRS_SHAPE_SPHERE 0u
+#define PBRS_SHAPE_MESH 1u
+
+// Row r of a 3x4 matrix = (c0[r], c1[r], c2[r], c3[r]) of the reference's column Mat4.
+struct InstTravRec {
+    float inv[3][4];
+    uint32_t shape_kind;
+    uint32_t shape_index;  // sphere record index / mesh header index
+    uint32_t identity;     // fwd == inv == I (add_instance got NULL matrices)
+    uint32_t pad;
+};
+static_assert(sizeof(InstTravRec) == 64, "InstTravRec must be 64 bytes");
+struct InstShadeRec {
+    float fwd[3][4];
+    uint32_t material;
+    uint32_t pad[3];
+};
+static_assert(sizeof(InstShadeRec) == 64, "InstShadeRec must be 64 bytes");
+
+// Per mesh: root box (tested with the incoming t_max, shape/src/blas.rs:428) and array bases.
+struct MeshRec {
+    float bmin[3], bmax[3];
+    uint32_t node_base;   // first NodeRec of this mesh in the BLAS node array
+    uint32_t tri_base;    // first TriRec
+    uint32_t n_tris;
+    uint32_t root_is_leaf;
+    uint32_t vert_base;   // first vertex in the attribute arrays
+    uint32_t idx_base;    // first triangle in the index array (indexed by TriRec::orig)
+    uint32_t pad[4];
+};
+static_assert(sizeof(MeshRec) == 64, "MeshRec must be 64 bytes");
+
+#define PBRS_TEX_SOLID 0
+#define PBRS_TEX_IMAGE 1
+#define PBRS_TEX_PERLIN 2
+struct TextureRec {
+    int32_t kind;
+    float value[3];
+    uint32_t width, height;
+    uint32_t texel_base;   // into the RGBA8 texel array
+    float freq;
+    uint32_t perlin_base;  // into the perlin table arrays (x256)
+    uint32_t pad[3];
+};
+
+struct MaterialRec {
+    int32_t kind;  // pbrs_material_kind
+    int32_t tex_kd, tex_ks, tex_kr, tex_kt;
+    float a[3], b[3];
+    float f[4];
+    int32_t remap;
+};
+
+#define PBRS_LIGHT_POINT 0
+#define PBRS_LIGHT_DISTANT 1
+struct DeltaLightRec {
+    int32_t kind;
+    float position[3];
+    float color[3];  // point: intensity; distant: radiance
+    float world_radius;
+    float casting_dir[3];
+    uint32_t pad;
+};
+#define PBRS_AREA_SPHERE 0
+#define PBRS_AREA_TRIANGLE 1
+struct AreaLightRec {
+    int32_t kind;
+    float p0[3];  // sphere: centre
+    float p1[3];  // sphere: (radius, -, -)
+    float p2[3];
+    float emit[3];
+    float area;
+    uint32_t pad[2];
+};
+
+#define PBRS_ENV_KIND_CONSTANT 0
+#define PBRS_ENV_KIND_FN 1
+#define PBRS_ENV_KIND_IMAGE 2
+
+// Camera constants (geometry/src/camera.rs:65-77): orientation * {a, b, c} precomputed on the host.
+struct CameraRec {
+    float center[3];
+    float a[3], b[3], c[3];
+    uint32_t width, height;
+};
+
+// Everything a kernel needs, passed by value.
+struct DeviceScene {
+    const NodeRec *tlas_nodes;
+    const NodeRec *blas_nodes;
+    const TriRec *tris;
+    const SphereRec *spheres;
+    const InstTravRec *inst_trav;
+    const InstShadeRec *inst_shade;
+    const MeshRec *meshes;
+    const float *vert_normals;  // 3 per vertex
+    const float *vert_uvs;      // 2 per vertex
+    const uint32_t *tri_idx;    // 3 per triangle, caller order
+    const MaterialRec *materials;
+    const TextureRec *textures;
+    const uint32_t *texels;     // RGBA8
+    const float *perlin_vec;    // 3 x 256 per perlin texture
+    const uint32_t *perlin_perm;  // 3 x 256 per perlin texture (x, y, z)
+    const DeltaLightRec *delta_lights;
+    const AreaLightRec *area_lights;
+    uint32_t n_delta, n_area, has_env;
+    int32_t env_kind, env_fn;
+    float env_color[3];
+    float env_scale[3];
+    TextureRec env_image;
+    CameraRec cam;
+    float tlas_min[3], tlas_max[3];
+    uint32_t tlas_root_is_leaf;  // a single instance
+    uint32_t n_instances;
+};
+
+}  // namespace pbrs

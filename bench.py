@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the pbrs path-tracing inner loop on B200s, next to the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1..c5] [--impl reference]
+
+A "step" is one full frame of the workload (every pixel, every sample, the bounce loop).  The
+scene is synthetic and procedurally generated (pbrs_b200/scenes.py), built once before timing.
+
+  value   Msamples/s, whole job, film left on the device (pbrs_render_device on torch's stream,
+          timed with CUDA events, max over ranks).  N > 1: the frame's 64x64 tiles (or its sample
+          indices for C5) are split over the ranks and the partial films summed with an NCCL
+          reduce inside the timed region -- total work fixed ("strong").
+  e2e     the same metric through pbrs_render with a HOST film buffer: the per-step host->device
+          traffic (tile list) and the device->host film copy are inside the timed region.
+  roofline  the closest-hit traversal kernel (k_extend): algorithmic bytes (SURVEY.md 8d formula,
+          counters from one untimed PBRS_FLAG_COUNT_TRAVERSAL frame) / its summed launch time
+          (CUDA events between launches, PBRS_FLAG_TIME_STAGES frames) vs the measured HBM copy peak.
+  cpu_baseline  the C++ oracle (a port: the Rust reference cannot be built here) on all host
+          threads, on a bounded row subset of the same frame.
+
+`--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Msamples/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def workload(name):
+    from pbrs_b200 import scenes
+    gen, integrator, msaa = scenes.CONFIGS[name]
+    return gen, integrator, msaa, scenes.WORKLOAD_NAMES[name]
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+def extend_bytes(st):
+    """32 (ray read) + 64/inner node + 48/triangle + 16/sphere + 128/instance + 32 (hit write)."""
+    n, t, s, i = st["trav_extend"]
+    return 64 * st["n_rays_extend"] + 64 * n + 48 * t + 16 * s + 128 * i
+
+
+def shadow_bytes(st):
+    n, t, s, i = st["trav_shadow"]
+    return 64 * st["n_rays_shadow"] + 64 * n + 48 * t + 16 * s + 128 * i
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(max(mx)); out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_sample(handle, integrator, msaa, target_s=12.0):
+    """Times the oracle on rows y0, y0+step, ... of the frame, step chosen for ~target_s of CPU work."""
+    from oracle import oracle_ffi
+    H, W = handle.height, handle.width
+    t0 = time.time()
+    probe_rows = max(1, H // 256)
+    _, st = oracle_ffi.render_rows(handle, max(1, H // probe_rows), integrator=integrator, msaa=msaa)
+    probe = max(time.time() - t0, 1e-4)
+    per_row = probe / max(1, len(range(0, H, max(1, H // probe_rows))))
+    rows = int(min(H, max(1, target_s / per_row)))
+    step = max(1, H // rows)
+    t0 = time.time()
+    _, st = oracle_ffi.render_rows(handle, step, integrator=integrator, msaa=msaa)
+    dt = time.time() - t0
+    n_rows = len(range(0, H, step))
+    return st, dt, n_rows, step
+
+
+def run_reference(args):
+    """The CPU path alone (oracle port of the reference, all host threads), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_ffi
+    gen, integrator, msaa, wname = workload(args.workload)
+    api = oracle_ffi.load()
+    h = gen().realize(api)
+    cores = api["get_threads"]()
+    H, W = h.height, h.width
+    # size the per-step sample for ~8 s
+    st, dt, n_rows, step = cpu_sample(h, integrator, msaa, target_s=8.0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.time()
+        _, st = oracle_ffi.render_rows(h, step, integrator=integrator, msaa=msaa)
+        if i >= args.warmup:
+            times.append(time.time() - t0)
+    dt = float(np.mean(times))
+    value = st["n_samples"] / dt / 1e6
+    rays = (st["n_rays_extend"] + st["n_rays_shadow"]) / dt / 1e6
+    sample = f"rows 0,{step},.. ({n_rows} of {H}) of the frame at full spp, per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, "integrator": integrator, "spp": msaa * msaa, "max_depth": 5, "sample": sample},
+        "mrays_per_s": rays,
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the pbrs CPU path (oracle/); the Rust reference cannot be built here"},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PBRS_BENCH_WORKLOAD", "c3"), choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--paths-in-flight", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from pbrs_b200 import _ffi
+    from pbrs_b200.dist import film_reduce, split_for
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pbrs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    gen, integrator, msaa, wname = workload(args.workload)
+    api = _ffi.load()
+    sd = gen()
+    h = sd.realize(api)
+    W, H = h.width, h.height
+    spp = msaa * msaa
+    split = split_for(args.workload)
+    kw = dict(integrator=integrator, msaa=msaa, max_depth=5, rank=rank, world_size=world, split=split, paths_in_flight=args.paths_in_flight)
+    film = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        h.render_device(film.data_ptr(), stream=stream.cuda_stream, flags=(8 if (world > 1 and split == "samples") else 0), **kw)
+        if world > 1:
+            film_reduce(film, spp if split == "samples" else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # untimed: traversal counters of this rank's share (for the roofline bytes)
+    st_count = h.render_device(film.data_ptr(), stream=stream.cuda_stream, want_stats=True, flags=1, **kw)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # roofline leg: per-stage launch times of this rank's share
+    st_time = None
+    for _ in range(max(1, min(args.steps, 3))):
+        s = h.render_device(film.data_ptr(), stream=stream.cuda_stream, want_stats=True, flags=2, **kw)
+        if st_time is None:
+            st_time = s
+        else:
+            for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total"):
+                st_time[k] = min(st_time[k], s[k])
+
+    # e2e leg: host film buffer, copies inside the timed region
+    host = np.zeros((H, W, 3), np.float32)
+    import ctypes as C
+    from pbrs_b200 import _capi as K
+    o = h.make_opts(**kw)
+    hp = host.ctypes.data_as(K.c_float_p)
+    for _ in range(args.warmup):
+        api["render"](h.ptr, C.byref(o), hp, None)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc = api["render"](h.ptr, C.byref(o), hp, None)
+        assert rc == 0, h.last_error()
+        if world > 1:
+            # host-side combine of the ranks' films: stage through the device film and NCCL
+            film.copy_(torch.from_numpy(host), non_blocking=False)
+            film_reduce(film, None)
+            if rank == 0:
+                host[...] = film.cpu().numpy()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_step = float(te.item()) / args.steps
+
+    # whole-job counts
+    cnt = torch.tensor([st_count["n_samples"], st_count["n_rays_extend"], st_count["n_rays_shadow"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt)
+    n_samples, n_ext, n_sh = [float(x) for x in cnt.tolist()]
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        ext_b = extend_bytes(st_count)
+        n_launch = max(1, st_time["launches_extend"])
+        ext_ms = st_time["ms_extend"]
+        achieved = ext_b / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        sh_ms = st_time["ms_shadow"]
+        line = {
+            "metric": METRIC, "value": n_samples / (ms_step * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wname, "integrator": integrator, "spp": spp, "max_depth": 5, "resolution": [W, H],
+                       "split": split if world > 1 else "none", "l2": "path state streamed per batch exceeds L2 (inputs larger than L2)",
+                       "paths_in_flight": args.paths_in_flight or (1 << 22)},
+            "mrays_per_s": (n_ext + n_sh) / (ms_step * 1e-3) / 1e6,
+            "frame_ms": ms_step,
+            "clocks": clk,
+            "e2e": {"value": n_samples / e2e_step / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_step * 1e3,
+                    "h2d_bytes_per_step": int(4 * ((W + 63) // 64) * ((H + 63) // 64)), "d2h_bytes_per_step": int(W * H * 12)},
+            "gpu_launches": int(st_time["launches"]) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS/BLAS walk)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": ext_b / n_launch, "ms_per_launch": ext_ms / n_launch, "launches_per_step": int(n_launch),
+                         "bytes_per_ray": ext_b / max(1.0, st_count["n_rays_extend"]),
+                         "note": "scene records are L2-resident for this workload; see DESIGN.md"},
+            "stages_ms": {k: st_time[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
+            "shadow_kernel": {"achieved": shadow_bytes(st_count) / (sh_ms * 1e-3) / 1e9 if sh_ms > 0 else 0.0, "unit": "GB/s"},
+            "would_panic": st_count["would_panic"],
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle_ffi
+            hc = sd.realize(oracle_ffi.load())
+            stc, dt, n_rows, step = cpu_sample(hc, integrator, msaa)
+            line["cpu_baseline"] = {"value": stc["n_samples"] / dt / 1e6, "unit": "Msamples/s", "cores": oracle_ffi.load()["get_threads"](), "kind": "port",
+                                    "sample": f"rows 0,{step},.. ({n_rows} of {H}) of the same frame at full spp, {dt:.1f} s",
+                                    "mrays_per_s": (stc["n_rays_extend"] + stc["n_rays_shadow"]) / dt / 1e6}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

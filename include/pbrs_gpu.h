@@ -184,6 +184,10 @@ typedef struct pbrs_stats {
     double ms_generate, ms_extend, ms_shade, ms_shadow, ms_accumulate; /* TIME_STAGES */
     uint64_t launches;      /* kernels launched by this call */
     uint64_t launches_extend;
+    /* the traversal counters again, split by kernel: {nodes, tris, spheres, instances} */
+    uint64_t trav_extend[4]; /* closest-hit walks (extend kernel) */
+    uint64_t trav_shadow[4]; /* any-hit walks (shadow kernel)     */
+    uint64_t launches_shadow;
 } pbrs_stats;
 
 /* would_panic indices */

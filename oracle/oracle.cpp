@@ -113,13 +113,28 @@ static bool tlas_occludes(const Scene &sc, const TlasNode *n, const Ray &ray) {
     if (g_diag) g_diag->n_nodes++;
     return tlas_occludes(sc, n->child[0].get(), ray) || tlas_occludes(sc, n->child[1].get(), ray);
 }
+struct TravSnapshot {
+    uint64_t v[4];
+    explicit TravSnapshot(const Diag &d) : v{d.n_nodes, d.n_tris, d.n_spheres, d.n_instances} {}
+    void charge(const Diag &d, uint64_t *dst) const {
+        dst[0] += d.n_nodes - v[0]; dst[1] += d.n_tris - v[1]; dst[2] += d.n_spheres - v[2]; dst[3] += d.n_instances - v[3];
+    }
+};
 static bool scene_intersect(const Scene &sc, Ray &ray, Hit *out) {
-    if (g_diag) g_diag->n_rays_extend++;
-    return tlas_intersect(sc, sc.tlas.get(), ray, out);
+    if (!g_diag) return tlas_intersect(sc, sc.tlas.get(), ray, out);
+    g_diag->n_rays_extend++;
+    TravSnapshot snap(*g_diag);
+    bool r = tlas_intersect(sc, sc.tlas.get(), ray, out);
+    snap.charge(*g_diag, g_diag->trav_extend);
+    return r;
 }
 static bool scene_occludes(const Scene &sc, const Ray &ray) {
-    if (g_diag) g_diag->n_rays_shadow++;
-    return tlas_occludes(sc, sc.tlas.get(), ray);
+    if (!g_diag) return tlas_occludes(sc, sc.tlas.get(), ray);
+    g_diag->n_rays_shadow++;
+    TravSnapshot snap(*g_diag);
+    bool r = tlas_occludes(sc, sc.tlas.get(), ray);
+    snap.charge(*g_diag, g_diag->trav_shadow);
+    return r;
 }
 
 // ---------------- environment: scene/src/lib.rs:96-117; scene/src/preset.rs:25-51 ----------------
@@ -691,6 +706,7 @@ static void fill_stats(pbrs_stats *st, const Diag &d, uint64_t n_samples, double
     st->n_rays_extend = d.n_rays_extend; st->n_rays_shadow = d.n_rays_shadow;
     st->n_nodes = d.n_nodes; st->n_tris = d.n_tris; st->n_spheres = d.n_spheres; st->n_instances = d.n_instances;
     for (int i = 0; i < 16; ++i) st->would_panic[i] = d.would_panic[i];
+    for (int i = 0; i < 4; ++i) { st->trav_extend[i] = d.trav_extend[i]; st->trav_shadow[i] = d.trav_shadow[i]; }
     st->ms_total = ms;
 }
 

@@ -28,7 +28,9 @@ struct Diag {
     uint64_t would_panic[16] = {0};
     uint64_t n_rays_extend = 0, n_rays_shadow = 0;
     uint64_t n_nodes = 0, n_tris = 0, n_spheres = 0, n_instances = 0;
+    uint64_t trav_extend[4] = {0, 0, 0, 0}, trav_shadow[4] = {0, 0, 0, 0};  // split by walk kind
     void add(const Diag &o) {
+        for (int i = 0; i < 4; ++i) { trav_extend[i] += o.trav_extend[i]; trav_shadow[i] += o.trav_shadow[i]; }
         for (int i = 0; i < 16; ++i) would_panic[i] += o.would_panic[i];
         n_rays_extend += o.n_rays_extend;
         n_rays_shadow += o.n_rays_shadow;

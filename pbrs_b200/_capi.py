@@ -69,10 +69,15 @@ class Stats(C.Structure):
         ("ms_shadow", C.c_double), ("ms_accumulate", C.c_double),
         ("launches", C.c_uint64),
         ("launches_extend", C.c_uint64),
+        ("trav_extend", C.c_uint64 * 4),
+        ("trav_shadow", C.c_uint64 * 4),
+        ("launches_shadow", C.c_uint64),
     ]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "would_panic"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("would_panic", "trav_extend", "trav_shadow")}
+        d["trav_extend"] = [int(v) for v in self.trav_extend]
+        d["trav_shadow"] = [int(v) for v in self.trav_shadow]
         d["would_panic"] = {PANIC_NAMES[i]: int(self.would_panic[i]) for i in range(NUM_PANIC_KINDS)
                             if self.would_panic[i]}
         return d

@@ -40,7 +40,8 @@ struct PathBuffers {
 };
 // counter block layout, per batch: [2*b] extend-queue length of bounce b, [2*b+1] shadow-queue length
 #define PBRS_COUNTS_PER_BATCH 32
-enum { kStatShadowRays = 0, kStatNodes = 1, kStatTris = 2, kStatSpheres = 3, kStatInsts = 4, kStatPanic0 = 8, kStatCount = 24 };
+// [kStatTrav + 4*k + {0..3}] = nodes, tris, spheres, instances of the closest-hit (k=0) / any-hit (k=1) walks
+enum { kStatShadowRays = 0, kStatTrav = 1, kStatPanic0 = 12, kStatCount = 28 };
 
 struct FrameParams {
     unsigned long long seed;

@@ -46,11 +46,12 @@ __device__ __forceinline__ void flush_diag(unsigned long long *stats, const Diag
             if (lane_id() == 0u) atomicAdd(stats + kStatPanic0 + k, (unsigned long long)c);
         }
 }
-__device__ __forceinline__ void flush_count(unsigned long long *stats, const TravCount &tc) {
-    warp_add_stat(stats + kStatNodes, tc.nodes);
-    warp_add_stat(stats + kStatTris, tc.tris);
-    warp_add_stat(stats + kStatSpheres, tc.spheres);
-    warp_add_stat(stats + kStatInsts, tc.insts);
+__device__ __forceinline__ void flush_count(unsigned long long *stats, const TravCount &tc, int which) {
+    unsigned long long *d = stats + kStatTrav + 4 * which;
+    warp_add_stat(d + 0, tc.nodes);
+    warp_add_stat(d + 1, tc.tris);
+    warp_add_stat(d + 2, tc.spheres);
+    warp_add_stat(d + 3, tc.insts);
 }
 
 // warp-uniform strided loop over [0, n): `body(idx, active)` runs with all 32 lanes converged
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kThreads) k_extend(DeviceScene sc, PathBuffers
     }
     __syncwarp();
     flush_diag(pb.stats, dg);
-    if (COUNT) flush_count(pb.stats, tc);
+    if (COUNT) flush_count(pb.stats, tc, 0);
 }
 
 __global__ void __launch_bounds__(kThreads) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, const uint32_t *queue,
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) k_shadow(DeviceScene sc, PathBuffers
     }
     __syncwarp();
     flush_diag(pb.stats, dg);
-    if (COUNT) flush_count(pb.stats, tc);
+    if (COUNT) flush_count(pb.stats, tc, 1);
 }
 
 __global__ void __launch_bounds__(kThreads) k_accumulate(PathBuffers pb, FrameParams fp, BatchParams bp, float *film) {
@@ -188,6 +189,7 @@ struct Workspace {
     uint32_t tiles_cap = 0;
     unsigned long long *stats = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> stage_ev;  // PBRS_FLAG_TIME_STAGES: boundaries between launches
     int sms = 0;
     Grid grid{};
     bool grid_ready = false;
@@ -200,6 +202,7 @@ void workspace_free(Workspace *w) {
     if (w->tiles) cudaFree(w->tiles);
     if (w->stats) cudaFree(w->stats);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : w->stage_ev) cudaEventDestroy(e);
     delete w;
 }
 
@@ -319,8 +322,26 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     if (tg.film) CK(cudaMemsetAsync(tg.film, 0, sizeof(float) * 3 * (size_t)W * H, stream));
     if (want_stats) CK(cudaEventRecord(w.ev[0], stream));
 
-    uint64_t launches = 0, launches_extend = 0;
+    uint64_t launches = 0, launches_extend = 0, launches_shadow = 0;
     const DeviceScene &sc = s.dscene;
+    // PBRS_FLAG_TIME_STAGES: one event after every launch; stage time = sum of the gaps that end
+    // with a launch of that stage (the stream is in order, so a gap is that kernel's duration).
+    const bool time_stages = want_stats && (o.flags & PBRS_FLAG_TIME_STAGES) != 0;
+    enum { T_GEN = 0, T_EXT = 1, T_SHADE = 2, T_SHADOW = 3, T_ACC = 4 };
+    std::vector<int> ev_kind;
+    size_t ev_used = 0;
+    auto mark = [&](int kind) -> int {
+        if (!time_stages) return 0;
+        if (ev_used == w.stage_ev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            w.stage_ev.push_back(e);
+        }
+        cudaEventRecord(w.stage_ev[ev_used++], stream);
+        ev_kind.push_back(kind);
+        return 0;
+    };
+    mark(-1);
     for (uint32_t b = 0; b < n_batches; ++b) {
         BatchParams bp;
         bp.first_pixel = b * ppb;
@@ -329,24 +350,28 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         pb.counts = w.counts + (size_t)b * PBRS_COUNTS_PER_BATCH;
         k_generate<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, pb.counts + 0);
         ++launches;
+        mark(T_GEN);
         for (int stage = 0; stage < n_stages; ++stage) {
             uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
             uint32_t *c_in = pb.counts + 2 * stage, *c_shadow = pb.counts + 2 * stage + 1, *c_out = pb.counts + 2 * (stage + 1);
             if (count_trav) k_extend<true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, c_in);
             else k_extend<false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, c_in);
             ++launches; ++launches_extend;
+            mark(T_EXT);
             if (tg.only_sample >= 0) break;
             k_shade<<<w.grid.shade, kThreads, 0, stream>>>(sc, pb, fp, bp, q_in, c_in, q_out, c_out, c_shadow, stage);
+            mark(T_SHADE);
             if (count_trav) k_shadow<true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, c_shadow);
             else k_shadow<false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, c_shadow);
-            launches += 2;
+            mark(T_SHADOW);
+            launches += 2; ++launches_shadow;
         }
         if (tg.only_sample >= 0) {
             k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
             ++launches;
         } else {
-            if (tg.film) { k_accumulate<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.film); ++launches; }
-            if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; }
+            if (tg.film) { k_accumulate<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.film); ++launches; mark(T_ACC); }
+            if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; mark(T_ACC); }
         }
     }
     CK(cudaGetLastError());
@@ -367,7 +392,20 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         for (uint32_t b = 0; b < n_batches; ++b) st->n_samples += counts[(size_t)b * PBRS_COUNTS_PER_BATCH];
         st->n_rays_extend = rays_extend;
         st->n_rays_shadow = stats[kStatShadowRays];
-        st->n_nodes = stats[kStatNodes]; st->n_tris = stats[kStatTris]; st->n_spheres = stats[kStatSpheres]; st->n_instances = stats[kStatInsts];
+        for (int k = 0; k < 4; ++k) { st->trav_extend[k] = stats[kStatTrav + k]; st->trav_shadow[k] = stats[kStatTrav + 4 + k]; }
+        st->n_nodes = st->trav_extend[0] + st->trav_shadow[0]; st->n_tris = st->trav_extend[1] + st->trav_shadow[1];
+        st->n_spheres = st->trav_extend[2] + st->trav_shadow[2]; st->n_instances = st->trav_extend[3] + st->trav_shadow[3];
+        st->launches_shadow = launches_shadow;
+        if (time_stages) {
+            double acc[5] = {0, 0, 0, 0, 0};
+            for (size_t i = 1; i < ev_used; ++i) {
+                float g = 0.0f;
+                CK(cudaEventElapsedTime(&g, w.stage_ev[i - 1], w.stage_ev[i]));
+                if (ev_kind[i] >= 0) acc[ev_kind[i]] += g;
+            }
+            st->ms_generate = acc[T_GEN]; st->ms_extend = acc[T_EXT]; st->ms_shade = acc[T_SHADE];
+            st->ms_shadow = acc[T_SHADOW]; st->ms_accumulate = acc[T_ACC];
+        }
         for (int k = 0; k < 16; ++k) st->would_panic[k] = stats[kStatPanic0 + k];
         st->ms_total = ms;
         st->launches = launches;

@@ -333,3 +333,82 @@ WORKLOAD_NAMES = {
     "c4": "C4 1M-triangle terrain 3840x2160 256spp path depth5",
     "c5": "C5 10k-instance field (~12.8M tris) 3840x2160 1024spp path depth5",
 }
+
+
+def perlin_tables(seed=SEED):
+    """Tables for Perlin::new (texture/src/lib.rs:66-96): 256 unit vectors, three permutations."""
+    rng = np.random.default_rng(seed)
+    v = rng.uniform(-1.0, 1.0, (256, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v.astype(np.float32), *(rng.permutation(256).astype(np.uint32) for _ in range(3))
+
+
+def material_zoo(width=160, height=120, env="image", delta_lights=True, seed=SEED):
+    """Every material, texture, light and environment kind of the ABI in one small scene: a ground
+    quad (Perlin marble), a back wall (image texture), a row of spheres and icospheres in each
+    material, a triangle area light + a sphere area light, a point and a distant light."""
+    rng = np.random.default_rng(seed)
+    sd = SceneDesc()
+    sd.set_camera(width, height, 45.0, (0.0, 3.0, -9.0), (0.0, 1.0, 0.0), (0, 1, 0))
+    rv, px, py, pz = perlin_tables(seed)
+    marble = sd.add_texture_perlin(1.5, rv, px, py, pz)
+    img = sd.add_texture_image(checker_noise_image(64, seed))
+    Pg, ig = _quad((-8, 0, -8), (8, 0, -8), (8, 0, 8), (-8, 0, 8))
+    UVg = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    sd.add_instance(sd.add_mesh(Pg, ig, UV=UVg), sd.lambertian(tex=marble))
+    Pw, iw = _quad((-8, 0, 6), (8, 0, 6), (8, 7, 6), (-8, 7, 6))
+    sd.add_instance(sd.add_mesh(Pw, iw, UV=UVg), sd.lambertian(tex=img))
+    white = sd.add_texture_solid((0.8, 0.8, 0.8))
+    spec = sd.add_texture_solid((0.4, 0.4, 0.4))
+    dark = sd.add_texture_solid((0.0, 0.0, 0.0))
+    mats = [
+        sd.lambertian((0.7, 0.3, 0.2)),
+        sd.metal(GOLD[0], GOLD[1], 0.15),
+        sd.metal(SILVER[0], SILVER[1], 0.0),
+        sd.glossy((0.6, 0.7, 0.9), 0.1),
+        sd.mirror((0.9, 0.9, 0.9)),
+        sd.dielectric(1.5),
+        sd.plastic((0.2, 0.5, 0.3), (0.3, 0.3, 0.3), 0.1),
+        sd.plastic((0.5, 0.2, 0.3), (0.3, 0.3, 0.3), 0.2, remap_roughness=False),
+        sd.uber(img, spec, tex_kr=spec, tex_kt=-1, rough_u=0.1, rough_v=0.2, eta=1.4, opacity=1.0),
+        sd.uber(white, spec, tex_kr=-1, tex_kt=spec, rough_u=0.05, rough_v=0.05, eta=1.3, opacity=0.6, remap_roughness=False),
+        sd.substrate(img, spec),
+        sd.uber(dark, dark, rough_u=0.1, rough_v=0.1),
+    ]
+    Pi, Ni, UVi, idxi = icosphere(2)
+    ico = sd.add_mesh(Pi, idxi, N=Ni, UV=UVi)
+    for k, m in enumerate(mats):
+        x = -5.5 + 1.0 * k
+        if k % 2 == 0:
+            sd.add_instance(sd.add_sphere((x, 0.5, 0.0 + 0.3 * (k % 3)), 0.5), m)
+        else:
+            fwd = translate((x, 0.55, 0.5)) @ rotate_axis((0.3, 1.0, 0.2), 0.7 * k) @ np.diag([0.5, 0.55, 0.45, 1.0])
+            sd.add_instance(ico, m, fwd=fwd)
+    # a triangle area light (two triangles of an emissive quad) and a sphere area light
+    L1 = (12.0, 11.0, 9.0)
+    q = np.array([(-2, 5, -1), (2, 5, -1), (2, 5, 2), (-2, 5, 2)], np.float32)
+    sd.add_instance(sd.add_mesh(q, np.array([[0, 2, 1], [0, 3, 2]], np.uint32)), sd.diffuse_light(L1))
+    sd.add_area_light_triangle(q[0], q[2], q[1], L1)
+    sd.add_area_light_triangle(q[0], q[3], q[2], L1)
+    c, r, L2 = (4.5, 3.0, -2.0), 0.6, (20.0, 20.0, 25.0)
+    sd.add_instance(sd.add_sphere((0, 0, 0), r), sd.diffuse_light(L2), fwd=translate(c))
+    sd.add_area_light_sphere(c, r, L2)
+    if delta_lights:
+        sd.add_point_light((-5.0, 4.0, -3.0), (30.0, 25.0, 20.0))
+        sd.add_distant_light((0.3, -1.0, 0.4), (0.8, 0.8, 0.9))
+    if env == "image":
+        g = np.linspace(0, 1, 32)
+        sky = np.zeros((16, 32, 3), np.uint8)
+        sky[..., 0] = (60 + 120 * g[None, :]).astype(np.uint8)
+        sky[..., 1] = (90 + 100 * np.linspace(1, 0, 16)[:, None]).astype(np.uint8)
+        sky[..., 2] = 200
+        sd.set_env_image(sky, (0.6, 0.6, 0.7))
+    elif env == "dusk":
+        sd.set_env_fn(K.ENV_DUSK)
+    elif env == "dark":
+        sd.set_env_fn(K.ENV_DARK_ROOM)
+    elif env == "black":
+        sd.set_env_constant((0.0, 0.0, 0.0))
+    else:
+        sd.set_env_constant((0.3, 0.3, 0.35))
+    return sd

@@ -23,3 +23,9 @@ def oracle_api():
 def gpu_api():
     from pbrs_b200 import _ffi
     return _ffi.load()
+
+
+@pytest.fixture(scope="session")
+def hostsim_api():
+    from tests import hostsim
+    return hostsim.load()

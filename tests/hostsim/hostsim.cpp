@@ -69,11 +69,13 @@ struct Sim {
 
 struct Totals {
     uint64_t samples = 0, rays_extend = 0, rays_shadow = 0, nodes = 0, tris = 0, spheres = 0, insts = 0;
+    uint64_t te[4] = {0, 0, 0, 0}, ts[4] = {0, 0, 0, 0};
     uint64_t panic[16] = {0};
     void add(const Totals &o) {
         samples += o.samples; rays_extend += o.rays_extend; rays_shadow += o.rays_shadow;
         nodes += o.nodes; tris += o.tris; spheres += o.spheres; insts += o.insts;
         for (int k = 0; k < 16; ++k) panic[k] += o.panic[k];
+        for (int k = 0; k < 4; ++k) { te[k] += o.te[k]; ts[k] += o.ts[k]; }
     }
 };
 void note(Totals &t, Diag &dg) {
@@ -104,6 +106,8 @@ void run_tiles(const SceneImpl &s, FrameParams fp, const std::vector<uint32_t> &
             TravCount tc{0, 0, 0, 0};
             tot.rays_extend += n_in;
             for (uint32_t i = 0; i < n_in; ++i) { stage_extend<true>(sc, pb, q_in[i], dg, tc); note(tot, dg); }
+            tot.te[0] += tc.nodes; tot.te[1] += tc.tris; tot.te[2] += tc.spheres; tot.te[3] += tc.insts;
+            const TravCount te_snapshot = tc;
             if (fp.only_sample >= 0) { tot.nodes += tc.nodes; tot.tris += tc.tris; tot.spheres += tc.spheres; tot.insts += tc.insts; break; }
             for (uint32_t i = 0; i < n_in; ++i) {
                 uint32_t j = q_in[i];
@@ -115,6 +119,8 @@ void run_tiles(const SceneImpl &s, FrameParams fp, const std::vector<uint32_t> &
                 tot.rays_shadow += (uint64_t)so.shadow_rays;
             }
             for (uint32_t i = 0; i < n_sh; ++i) { stage_shadow<true>(sc, pb, pb.shadow_queue[i], dg, tc); note(tot, dg); }
+            tot.ts[0] += tc.nodes - te_snapshot.nodes; tot.ts[1] += tc.tris - te_snapshot.tris;
+            tot.ts[2] += tc.spheres - te_snapshot.spheres; tot.ts[3] += tc.insts - te_snapshot.insts;
             tot.nodes += tc.nodes; tot.tris += tc.tris; tot.spheres += tc.spheres; tot.insts += tc.insts;
             n_in = n_out;
         }
@@ -195,6 +201,7 @@ int run(const pbrs_scene *scene, const pbrs_render_opts &o, float *film, float *
         st->n_samples = tot.samples; st->n_rays_extend = tot.rays_extend; st->n_rays_shadow = tot.rays_shadow;
         st->n_nodes = tot.nodes; st->n_tris = tot.tris; st->n_spheres = tot.spheres; st->n_instances = tot.insts;
         for (int k = 0; k < 16; ++k) st->would_panic[k] = tot.panic[k];
+        for (int k = 0; k < 4; ++k) { st->trav_extend[k] = tot.te[k]; st->trav_shadow[k] = tot.ts[k]; }
     }
     return 0;
 }

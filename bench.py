@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("PBRS_BENCH_WORKLOAD", "c3"), choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--paths-in-flight", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--frame-scale", type=float, default=1.0, help="shrink the frame (profiling runs only; 1.0 = the BASELINE size)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -199,7 +200,9 @@ def main():
 
     gen, integrator, msaa, wname = workload(args.workload)
     api = _ffi.load()
-    sd = gen()
+    sd = gen(args.frame_scale)
+    if args.frame_scale != 1.0:
+        wname += f" [frame scaled x{args.frame_scale}: NOT the BASELINE size]"
     h = sd.realize(api)
     W, H = h.width, h.height
     spp = msaa * msaa

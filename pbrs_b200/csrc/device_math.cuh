@@ -15,11 +15,16 @@
 #include <stdint.h>
 #include <string.h>
 
+// PB_CALL marks the large shading functions that are kept as real calls on the device: the shade
+// kernel is instruction-cache bound when everything is inlined (ncu: stall_no_instruction dominant,
+// profiles/r1_v0_*), and one copy of each lobe / transcendental routine fixes that.
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define PB_DEV __host__ __device__ __forceinline__
+#define PB_CALL __host__ __device__ __noinline__
 #else
 #define PB_DEV inline
+#define PB_CALL inline
 #endif
 
 namespace pbrs {
@@ -74,14 +79,14 @@ PB_DEV bool sign_neg(float x) { return (f2u(x) >> 31) != 0u; }
 // decision downstream (a Fresnel coin, a shadow test), so shading evaluates them in FP64 and
 // rounds once: this agrees with glibc in all but ~1e-3 of calls.  B200 has full-rate-class
 // FP64 and these sit only in shading, never in traversal.
-PB_DEV float t_sin(float x) { return (float)sin((double)x); }
-PB_DEV float t_cos(float x) { return (float)cos((double)x); }
-PB_DEV float t_tan(float x) { return (float)tan((double)x); }
-PB_DEV float t_atan(float x) { return (float)atan((double)x); }
-PB_DEV float t_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
-PB_DEV float t_acos(float x) { return (float)acos((double)x); }
-PB_DEV float t_log(float x) { return (float)log((double)x); }
-PB_DEV float t_exp(float x) { return (float)exp((double)x); }
+PB_CALL float t_sin(float x) { return (float)sin((double)x); }
+PB_CALL float t_cos(float x) { return (float)cos((double)x); }
+PB_CALL float t_tan(float x) { return (float)tan((double)x); }
+PB_CALL float t_atan(float x) { return (float)atan((double)x); }
+PB_CALL float t_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+PB_CALL float t_acos(float x) { return (float)acos((double)x); }
+PB_CALL float t_log(float x) { return (float)log((double)x); }
+PB_CALL float t_exp(float x) { return (float)exp((double)x); }
 PB_DEV float t_hypot(float x, float y) { return (float)sqrt((double)x * (double)x + (double)y * (double)y); }
 
 // per-thread diagnostics: reference asserts that would have fired (bit k = kind k)

@@ -74,7 +74,7 @@ PB_DEV float fresnel_refl_coeff(const Lobe &f, float cos_i, Diag &dg) {
     float r_par = (eta_t * cos_i - eta_i * cos_t) / (eta_t * cos_i + eta_i * cos_t);
     return (r_par * r_par + r_perp * r_perp) * 0.5f;
 }
-PB_DEV color fresnel_eval(const Lobe &f, float cos_i, Diag &dg) {
+PB_CALL color fresnel_eval(const Lobe &f, float cos_i, Diag &dg) {
     if (f.fresnel != FR_CONDUCTOR) return grayc(fresnel_refl_coeff(f, cos_i, dg));
     color eta_i = grayc(1.0f);
     color eta = cw_div(f.eta_t, eta_i);
@@ -105,7 +105,7 @@ PB_DEV float roughness_to_alpha(float roughness) {
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 // :36-59
-PB_DEV float mf_d(float ax, float ay, vec3 wh, Diag &dg) {
+PB_CALL float mf_d(float ax, float ay, vec3 wh, Diag &dg) {
     float tan2 = tan2_theta(wh);
     float c2 = cos2_theta(wh);
     float cos4 = c2 * c2;
@@ -115,7 +115,7 @@ PB_DEV float mf_d(float ax, float ay, vec3 wh, Diag &dg) {
     return t_exp(x * -tan2) / (kPi * ax * ay * cos4);
 }
 // :64-88
-PB_DEV float mf_lambda(float ax, float ay, vec3 w) {
+PB_CALL float mf_lambda(float ax, float ay, vec3 w) {
     float abs_tan = fabsf(sqrtf(tan2_theta(w)));
     if (is_inf(abs_tan)) return 0.0f;
     float alpha = sqrtf(cos2_phi(w) * (ax * ax) + sin2_phi(w) * (ay * ay));
@@ -133,7 +133,7 @@ PB_DEV float mf_pdf(float ax, float ay, vec3 wh, Diag &dg) {
     return d * y;
 }
 // :126-159
-PB_DEV vec3 mf_sample_wh(float ax, float ay, vec3 wo, float u, float v, Diag &dg) {
+PB_CALL vec3 mf_sample_wh(float ax, float ay, vec3 wo, float u, float v, Diag &dg) {
     float tan2, phi;
     float log_sample = t_log(1.0f - u);
     if (!is_fin(log_sample)) flag(dg, P_LOG_SAMPLE);
@@ -179,7 +179,7 @@ PB_DEV void specular_refract(const Lobe &l, vec3 wo, vec3 &wi, color &c, Diag &d
     c = (f_tr / fabsf(cos_theta(t))) * l.albedo;
 }
 // :458-460, 540-559 (Lambert only: Oren-Nayar is never instantiated by a material), 594-609
-PB_DEV color lobe_eval(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
+PB_CALL color lobe_eval(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
     if (l.kind == LOBE_SPECULAR) return blackc();
     if (l.kind == LOBE_LAMBERT) return l.albedo * kInvPi;
     float cto = fabsf(cos_theta(wo));
@@ -192,7 +192,7 @@ PB_DEV color lobe_eval(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
     return l.albedo * mf_d(l.ax, l.ay, wh, dg) * mf_g(l.ax, l.ay, wo, wi) * refl * weak_recip(4.0f * cto * cti);
 }
 // :503-505, 566-572 (Q6), 628-638
-PB_DEV Prob lobe_prob(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
+PB_CALL Prob lobe_prob(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
     if (l.kind == LOBE_SPECULAR) return Mass(0.0f);
     if (l.kind == LOBE_LAMBERT) {
         if (wo.z * wi.z >= 0.0f) return Density(wi.z * kInvPi);
@@ -204,7 +204,7 @@ PB_DEV Prob lobe_prob(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
     return Density(0.0f);
 }
 // :462-501, 560-564, 611-626
-PB_DEV void lobe_sample(const Lobe &l, vec3 wo, float r0, float r1, color &f, vec3 &wi, Prob &pr, Diag &dg) {
+PB_CALL void lobe_sample(const Lobe &l, vec3 wo, float r0, float r1, color &f, vec3 &wi, Prob &pr, Diag &dg) {
     if (l.kind == LOBE_SPECULAR) {
         if (l.intrusion == INTR_REFLECTION) {
             specular_reflect(l, wo, wi, f, dg);
@@ -240,7 +240,7 @@ PB_DEV color unpack_rgb8(uint32_t p) {  // Color::rgb(u8,u8,u8), radiometry/src/
     return mkc((float)(p & 255u) / 255.0f, (float)((p >> 8) & 255u) / 255.0f, (float)((p >> 16) & 255u) / 255.0f);
 }
 // lib.rs:98-138
-PB_DEV float perlin_noise(const DeviceScene &sc, const TextureRec &t, vec3 p, Diag &dg) {
+PB_CALL float perlin_noise(const DeviceScene &sc, const TextureRec &t, vec3 p, Diag &dg) {
     float fx = p.x * t.freq, fy = p.y * t.freq, fz = p.z * t.freq;
     float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     int i = (int)flx, j = (int)fly, k = (int)flz;
@@ -285,7 +285,7 @@ PB_DEV color image_lookup(const DeviceScene &sc, const TextureRec &t, float u, f
     uint32_t row = (fv > 0.0f ? (uint32_t)fv : 0u) % t.height;
     return unpack_rgb8(ld_u32(sc.texels + t.texel_base + row * t.width + col));
 }
-PB_DEV color texture_value(const DeviceScene &sc, int id, float u, float v, vec3 p, Diag &dg) {
+PB_CALL color texture_value(const DeviceScene &sc, int id, float u, float v, vec3 p, Diag &dg) {
     const TextureRec &t = sc.textures[id];
     if (t.kind == PBRS_TEX_SOLID) return mkc(t.value[0], t.value[1], t.value[2]);  // :29-33
     if (t.kind == PBRS_TEX_IMAGE) return image_lookup(sc, t, u, v);
@@ -314,7 +314,7 @@ PB_DEV Lobe mk_microfacet(color albedo, float ax, float ay) {
 PB_DEV color mtl_emission(const MaterialRec &m) {  // :291-299
     return m.kind == PBRS_MTL_DIFFUSE_LIGHT ? mkc(m.a[0], m.a[1], m.a[2]) : blackc();
 }
-PB_DEV void bxdfs_at(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
+PB_CALL void bxdfs_at(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
     L.n = 0;
     color ca = mkc(m.a[0], m.a[1], m.a[2]), cb = mkc(m.b[0], m.b[1], m.b[2]);
     switch (m.kind) {
@@ -396,7 +396,7 @@ PB_DEV Frame bsdf_frame(const Isect &h, Diag &dg) {  // :18-31, :125-137
 }
 PB_DEV vec3 to_local(const Frame &f, vec3 w, Diag &dg) { return hat(mk(dot(f.t, w), dot(f.b, w), dot(f.n, w)), dg); }  // :113-117
 PB_DEV vec3 to_world(const Frame &f, vec3 l) { return l.x * f.t + l.y * f.b + l.z * f.n; }                           // :119-123
-PB_DEV color bsdf_eval(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :43-51
+PB_CALL color bsdf_eval(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :43-51
     vec3 wi = to_local(fr, wi_w, dg);
     vec3 wo = to_local(fr, wo_w, dg);
     if (wo.z == 0.0f) return blackc();
@@ -404,7 +404,7 @@ PB_DEV color bsdf_eval(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Di
     for (int i = 0; i < L.n; ++i) s = s + lobe_eval(L.l[i], wo, wi, dg);
     return s;
 }
-PB_DEV float bsdf_pdf(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :53-57 (Q4: a sum)
+PB_CALL float bsdf_pdf(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :53-57 (Q4: a sum)
     vec3 wi = to_local(fr, wi_w, dg);
     vec3 wo = to_local(fr, wo_w, dg);
     float s = 0.0f;
@@ -416,7 +416,7 @@ PB_DEV float bsdf_pdf(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Dia
 }
 // :59-103.  The chosen lobe is swap_remove()d from the list: the rest are visited with the last
 // lobe moved into the chosen slot.
-PB_DEV void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr,
+PB_CALL void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr,
                         Diag &dg) {
     if (!(u < 1.0f)) flag(dg, P_MISC);
     vec3 wo = to_local(fr, wo_world, dg);
@@ -464,7 +464,7 @@ PB_DEV bool bsdf_sample_specular(const Frame &fr, const Lobes &L, vec3 wo_world,
 }
 
 // ---- environment: scene/src/lib.rs:96-117; scene/src/preset.rs:25-51 ----
-PB_DEV color eval_env(const DeviceScene &sc, vec3 dir, Diag &dg) {
+PB_CALL color eval_env(const DeviceScene &sc, vec3 dir, Diag &dg) {
     if (sc.env_kind == PBRS_ENV_KIND_CONSTANT) return mkc(sc.env_color[0], sc.env_color[1], sc.env_color[2]);
     if (sc.env_kind == PBRS_ENV_KIND_IMAGE) {
         float phi = t_atan2(dir.z, dir.x);
@@ -505,7 +505,7 @@ PB_DEV void sphere_sample(vec3 c, float radius, float u, float v, vec3 &pos, vec
     normal = dir;
 }
 // :197-236
-PB_DEV void sphere_sample_towards(vec3 c, float radius, vec3 target, float u, float v, vec3 &pos, vec3 &normal, Diag &dg) {
+PB_CALL void sphere_sample_towards(vec3 c, float radius, vec3 target, float u, float v, vec3 &pos, vec3 &normal, Diag &dg) {
     vec3 wc = c - target;
     float r2 = radius * radius;
     if (len2(wc) < r2) { sphere_sample(c, radius, u, v, pos, normal); return; }
@@ -565,7 +565,7 @@ PB_DEV AreaLight load_area_light(const AreaLightRec *r) {
     l.area = r->area;
     return l;
 }
-PB_DEV bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, vec3 &normal, Diag &dg) {
+PB_CALL bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, vec3 &normal, Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) {
         Isect h;
         if (!sphere_intersect(l.p0, l.p1.x, r, h, dg)) return false;
@@ -575,7 +575,7 @@ PB_DEV bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, ve
     return isotri_intersect(l.p0, l.p1, l.p2, r, pos, normal, dg);
 }
 // sample_shape.rs:28-33 default pdf_at (Q12: distance, not distance squared); sphere override :238
-PB_DEV bool area_shape_pdf_at(const AreaLight &l, const Isect &ref, vec3 wi, float &pdf, Diag &dg) {
+PB_CALL bool area_shape_pdf_at(const AreaLight &l, const Isect &ref, vec3 wi, float &pdf, Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) return sphere_pdf_at(l.p0, l.p1.x, ref.pos, wi, pdf);
     Ray ray = spawn_ray(ref, wi);
     vec3 pos, normal;

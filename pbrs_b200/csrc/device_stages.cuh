@@ -14,6 +14,7 @@
 // is why a shadow entry carries the candidate contributions instead of a boolean.
 #pragma once
 #include "device_shade.cuh"
+#include "device_walk.cuh"
 
 namespace pbrs {
 
@@ -38,8 +39,10 @@ struct PathBuffers {
     unsigned long long *stats;     // kStat* accumulators of the whole call
     uint32_t capacity;
 };
-// counter block layout, per batch: [2*b] extend-queue length of bounce b, [2*b+1] shadow-queue length
-#define PBRS_COUNTS_PER_BATCH 32
+// counter block layout, per batch: [2*b] extend-queue length of bounce b, [2*b+1] shadow-queue length,
+// [32+b] / [48+b] the work cursors the persistent extend / shadow kernels of bounce b draw rays from
+#define PBRS_COUNTS_PER_BATCH 64
+#define PBRS_MAX_STAGES 15
 // [kStatTrav + 4*k + {0..3}] = nodes, tris, spheres, instances of the closest-hit (k=0) / any-hit (k=1) walks
 enum { kStatShadowRays = 0, kStatTrav = 1, kStatPanic0 = 12, kStatCount = 28 };
 
@@ -149,26 +152,31 @@ PB_DEV Ray load_ray(const PathBuffers &pb, uint32_t j) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// extend: scene.tlas.intersect(&mut ray) (tlas/src/bvh.rs:77)
+// extend: scene.tlas.intersect(&mut ray) (tlas/src/bvh.rs:77).  The walk itself is device_walk.cuh;
+// these are its two ends.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-PB_DEV void stage_extend(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
-    Ray ray = load_ray(pb, j);
-    Hit h;
-    tlas_closest<COUNT>(sc, ray, h, dg, tc);
-    u4 rec; rec.x = f2u(h.t); rec.y = h.inst; rec.z = h.tri; rec.w = 0u;
+PB_DEV void store_hit(const PathBuffers &pb, uint32_t j, const Hit &h) {
 #ifdef __CUDA_ARCH__
-    *reinterpret_cast<uint4 *>(pb.hit + j) = make_uint4(rec.x, rec.y, rec.z, rec.w);
+    *reinterpret_cast<uint4 *>(pb.hit + j) = make_uint4(f2u(h.t), h.inst, h.tri, 0u);
 #else
+    u4 rec; rec.x = f2u(h.t); rec.y = h.inst; rec.z = h.tri; rec.w = 0u;
     pb.hit[j] = rec;
 #endif
+}
+template <bool COUNT>
+PB_DEV void stage_extend(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
+    uint32_t st_ref[PBRS_WALK_STACK], st_par[PBRS_WALK_STACK];
+    float st_tl[PBRS_WALK_STACK];
+    Walk<false, COUNT> w(st_ref, st_tl, st_par);
+    w.run(sc, load_ray(pb, j), dg, tc);
+    store_hit(pb, j, w.best);
 }
 
 // Rebuilds the world-space Interaction of a recorded hit: Instance::intersect (tlas/src/instance.rs:50-72)
 // = ray to object space, the shape's own intersect for the winning primitive, hit back to world
 // (geometry/src/transform.rs:309-320).  Same inputs, same operations as during the walk, so the
 // values equal what the reference computed when it found the hit.
-PB_DEV void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32_t inst, uint32_t tri, Isect &out, uint32_t &material,
+PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32_t inst, uint32_t tri, Isect &out, uint32_t &material,
                             Diag &dg) {
     Ray wr = world_ray;
     wr.t_max = PB_INF;
@@ -215,7 +223,7 @@ PB_DEV float power_heuristic2(float nf, float f_pdf, float ng, float g_pdf) {  /
     float f = nf * f_pdf, g = ng * g_pdf;
     return (f * f) / (f * f + g * g);
 }
-PB_DEV int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
+PB_CALL int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
                             ShadowOut &so, Diag &dg) {
     so.has1 = so.has2 = false;
     uint32_t nd = sc.n_delta, na = sc.n_area;
@@ -471,26 +479,41 @@ PB_DEV ShadeOut stage_shade_direct(const DeviceScene &sc, const PathBuffers &pb,
 // shadow: scene.tlas.occludes(&vis_ray) for the entry's rays, then the radiance update of
 // src/pathintegrator.rs:35 / src/directlighting.rs:36,44.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-PB_DEV void stage_shadow(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
-    f4 o1 = load_f4(pb.sh_o1 + j), d1 = load_f4(pb.sh_d1 + j), o2 = load_f4(pb.sh_o2 + j), d2 = load_f4(pb.sh_d2 + j);
-    f4 cc = load_f4(pb.sh_c + j), mb = load_f4(pb.sh_b + j);
+// ray `which` (0/1) of path j's shadow entry; false if absent
+PB_DEV bool shadow_ray(const PathBuffers &pb, uint32_t j, int which, Ray &r) {
+    f4 o = load_f4((which ? pb.sh_o2 : pb.sh_o1) + j);
+    if (o.w < 0.0f) return false;
+    f4 d = load_f4((which ? pb.sh_d2 : pb.sh_d1) + j);
+    r.o = mk(o.x, o.y, o.z); r.d = mk(d.x, d.y, d.z); r.t_max = o.w;
+    return true;
+}
+// vis: bit 0 / 1 = ray 1 / 2 was traced and found unoccluded
+PB_DEV void shadow_finish(const PathBuffers &pb, uint32_t j, uint32_t vis) {
+    f4 d1 = load_f4(pb.sh_d1 + j), d2 = load_f4(pb.sh_d2 + j), cc = load_f4(pb.sh_c + j), mb = load_f4(pb.sh_b + j);
     float mode = pb.sh_m[j];
     color ld = blackc();
-    if (!(o1.w < 0.0f)) {
-        Ray r; r.o = mk(o1.x, o1.y, o1.z); r.d = mk(d1.x, d1.y, d1.z); r.t_max = o1.w;
-        if (!tlas_any<COUNT>(sc, r, dg, tc)) ld = ld + mkc(d1.w, cc.x, cc.y);
-    }
-    if (!(o2.w < 0.0f)) {
-        Ray r; r.o = mk(o2.x, o2.y, o2.z); r.d = mk(d2.x, d2.y, d2.z); r.t_max = o2.w;
-        if (!tlas_any<COUNT>(sc, r, dg, tc)) ld = ld + mkc(d2.w, cc.z, cc.w);
-    }
+    if (vis & 1u) ld = ld + mkc(d1.w, cc.x, cc.y);
+    if (vis & 2u) ld = ld + mkc(d2.w, cc.z, cc.w);
     color x = ld * mb.w;  // one_light_incident_radiance * (1.0 / light_pdf)
     f4 rd = load_f4(pb.rad + j);
     color radiance = mkc(rd.x, rd.y, rd.z), mult = mkc(mb.x, mb.y, mb.z);
     if (mode < 0.0f) radiance = radiance + mult * x;
     else radiance = radiance + x * mult * mode;
     store_f4(pb.rad + j, radiance.r, radiance.g, radiance.b, 0.0f);
+}
+template <bool COUNT>
+PB_DEV void stage_shadow(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
+    uint32_t vis = 0u;
+    uint32_t st_ref[PBRS_WALK_STACK], st_par[1];
+    float st_tl[1];
+    for (int which = 0; which < 2; ++which) {
+        Ray r;
+        if (!shadow_ray(pb, j, which, r)) continue;
+        Walk<true, COUNT> w(st_ref, st_tl, st_par);
+        w.run(sc, r, dg, tc);
+        if (!w.occluded) vis |= 1u << which;
+    }
+    shadow_finish(pb, j, vis);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,321 @@
+// The traversal kernels' walker: closest-hit and any-hit walks of the two-level BVH as ONE
+// resumable state machine per lane.
+//
+// Why a state machine: in SIMT the naive nesting (TLAS loop -> instance -> BLAS loop -> leaf)
+// lets a lane that is deep inside a mesh run alone while its 31 neighbours wait at the TLAS
+// level (ncu on the first version: 7-11 of 32 lanes active, profiles/r1_v0_*).  Here every
+// lane, whatever level it is on, meets the others in the same two phases of `step()`:
+//     phase 1  while the lane's next visit is an inner node: fetch its 64-byte record, test both
+//              child boxes, choose / push                       (the hot loop, shared by TLAS and BLAS)
+//     phase 2  one leaf (triangle run, sphere, or instance entry) or one stack unwind
+// and the kernels (kernels.cu) refill finished lanes from the ray queue between steps.
+//
+// Exactness (DESIGN.md "Traversal"): the visit order, the extent each box/primitive is tested
+// against and every tie-break equal the reference's walks (tlas/src/bvh.rs:77-113,
+// shape/src/blas.rs:422-495, incl. quirks Q14/Q17).  The box test is the reference's slab test
+// (geometry/src/bvh.rs:84-99, true divisions); a reciprocal-multiply pre-test decides the clear
+// cases and hands everything within a few ulps of the boundary to the exact divisions, so the
+// pass/fail outcome of every box is bit-identical to the reference's.
+#pragma once
+#include "device_geom.cuh"
+
+namespace pbrs {
+
+#define PBRS_NONE 0xFFFFFFFFu
+#define PBRS_TAG_COMBINE 0x40000000u  // TLAS closest: [lv] left value waiting for the right subtree's
+#define PBRS_TAG_EXIT 0x20000000u     // closest: boundary between the TLAS entries and a mesh walk's
+#define PBRS_WALK_STACK 160
+
+// relative margin of the pre-test: the product (mn - o) * fl(1/d) is within 1.5 * 2^-23 of the
+// quotient fl((mn - o) / d); 8 * 2^-23 leaves a 5x safety factor
+#define PBRS_BOX_MARGIN 9.5367431640625e-7f
+#define PBRS_BOX_TINY 1e-30f
+
+struct BoxTest {
+    bool pass;     // t_low <= min(min_el, t_max): exactly the reference's outcome
+    bool overlap;  // !(t_low > min_el): could pass under a larger extent
+    float tl;      // t_low, approximate (within the margin) or exact
+};
+
+// One child box against the ray.  `fast` = the ray's direction has no zero / non-finite
+// reciprocal, so the products below are finite or overflow to inf (never NaN).
+PB_DEV BoxTest test_box(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 o, vec3 d, vec3 rd, bool fast, float t_max) {
+    BoxTest r;
+    if (fast) {
+        float ax = (mnx - o.x) * rd.x, bx = (mxx - o.x) * rd.x;
+        float ay = (mny - o.y) * rd.y, by = (mxy - o.y) * rd.y;
+        float az = (mnz - o.z) * rd.z, bz = (mxz - o.z) * rd.z;
+        float tl = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), 0.0f);
+        float me = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        float m_tl = PBRS_BOX_MARGIN * tl + PBRS_BOX_TINY;            // tl >= 0
+        float m_me = PBRS_BOX_MARGIN * fabsf(me) + PBRS_BOX_TINY;
+        bool ov_yes = tl + m_tl <= me - m_me, ov_no = tl - m_tl > me + m_me;
+        bool t_yes = tl + m_tl <= t_max, t_no = tl - m_tl > t_max;
+        if ((ov_yes || ov_no) && (t_yes || t_no)) {  // false whenever tl or me is inf / NaN
+            r.pass = ov_yes && t_yes;
+            r.overlap = ov_yes;
+            r.tl = tl;
+            return r;
+        }
+    }
+    Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
+    float tl, me;
+    slab(mnx, mny, mnz, mxx, mxy, mxz, ray, tl, me);
+    r.pass = box_pass(tl, me, t_max);
+    r.overlap = !(tl > me);
+    r.tl = tl;
+    return r;
+}
+// Re-test of a stacked child against the extent of the moment (it overlapped when pushed):
+// pass iff t_low <= t_max.  Returns 1 pass, 0 fail, -1 too close to call with an approximate tl.
+PB_DEV int retest(float tl, float t_max) {
+    float m = PBRS_BOX_MARGIN * tl + PBRS_BOX_TINY;
+    if (tl + m <= t_max) return 1;
+    if (tl - m > t_max) return 0;
+    return -1;
+}
+
+template <bool ANY, bool COUNT>
+struct Walk {
+    // ray in the current space (world on the TLAS level, object inside a mesh instance)
+    vec3 o, d, rd;
+    float t_max;
+    bool fast;
+    // the world ray while inside an instance
+    vec3 wo, wd;
+    float w_t_max;
+    uint32_t next;  // ref to visit (PBRS_LEAF_BIT = leaf), PBRS_NONE = unwind
+    uint32_t lvl;   // 0 = TLAS, 1 = inside a mesh instance
+    int sp;
+    bool done;
+    // closest: running winner ("smallest t, right-most on ties"); any: occluded
+    Hit best;
+    bool occluded;
+    // the mesh instance being walked
+    float l_best_t;
+    uint32_t l_best_tri, cur_inst;
+    MeshHead mesh;
+    float ret;  // TLAS closest: value of the subtree that just completed
+    // the stack lives in arrays owned by the caller (so that the scalars above stay in registers)
+    uint32_t *st_ref;
+    float *st_tl;
+    uint32_t *st_par;  // parent node (| side in bit 31) for the rare exact re-test
+
+    PB_DEV Walk(uint32_t *ref, float *tl, uint32_t *par) : st_ref(ref), st_tl(tl), st_par(par) {}
+
+    PB_DEV void set_space(vec3 no, vec3 nd, float nt) {
+        o = no; d = nd; t_max = nt;
+        rd = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        fast = is_fin(rd.x) && is_fin(rd.y) && is_fin(rd.z) && !any_nan(o);
+    }
+    PB_DEV void push(uint32_t ref, float tl, uint32_t par, Diag &dg) {
+        if (sp < PBRS_WALK_STACK) {
+            st_ref[sp] = ref;
+            if (!ANY) { st_tl[sp] = tl; st_par[sp] = par; }  // any-hit entries are bare refs
+            ++sp;
+        } else {
+            flag(dg, P_STACK);
+        }
+    }
+    PB_DEV const NodeRec *node_ptr(const DeviceScene &sc, uint32_t idx) const {
+        return lvl ? sc.blas_nodes + mesh.node_base + idx : sc.tlas_nodes + idx;
+    }
+    // exact t_low / pass of child `side` of node `par` (the rare re-test)
+    PB_DEV bool exact_child(const DeviceScene &sc, uint32_t par, float extent) const {
+        const char *b = reinterpret_cast<const char *>(node_ptr(sc, par & 0x7FFFFFFFu));
+        f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32);
+        Ray ray; ray.o = o; ray.d = d; ray.t_max = extent;
+        float tl, me;
+        if (par & 0x80000000u) slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ray, tl, me);
+        else slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ray, tl, me);
+        return box_pass(tl, me, extent);
+    }
+
+    // ---- start: the root box with the ray's own extent (tlas/src/bvh.rs:78,106) ----
+    PB_DEV void begin(const DeviceScene &sc, const Ray &ray) {
+        set_space(ray.o, ray.d, ray.t_max);
+        lvl = 0u; sp = 0; done = false; occluded = false; ret = PB_INF;
+        best.t = PB_INF; best.inst = PBRS_NONE; best.tri = PBRS_NONE;
+        BoxTest b = test_box(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], o, d, rd, fast, t_max);
+        if (!b.pass) { done = true; next = PBRS_NONE; return; }
+        next = sc.tlas_root_is_leaf ? PBRS_LEAF_BIT : 0u;
+    }
+
+    PB_DEV bool at_inner() const { return !done && next != PBRS_NONE && !(next & PBRS_LEAF_BIT); }
+
+    // ---- phase 1: expand the inner node `next` ----
+    PB_DEV void expand(const DeviceScene &sc, Diag &dg, TravCount &tc) {
+        if (COUNT) tc.nodes++;
+        const uint32_t self = next;
+        const char *b = reinterpret_cast<const char *>(node_ptr(sc, self));
+        f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32), q3 = ld16(b + 48);
+        BoxTest L = test_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, rd, fast, t_max);
+        BoxTest R = test_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, rd, fast, t_max);
+        uint32_t meta = f2u(q3.z);
+        uint32_t lref = f2u(q3.x) | ((meta & PBRS_NODE_LEFT_LEAF) ? PBRS_LEAF_BIT : 0u);
+        uint32_t rref = f2u(q3.y) | ((meta & PBRS_NODE_RIGHT_LEAF) ? PBRS_LEAF_BIT : 0u);
+        if (ANY) {
+            // `left || right`, depth first; the extent never changes, so a pass is final
+            if (L.pass) {
+                if (R.pass) push(rref, 0.0f, 0u, dg);
+                next = lref;
+            } else {
+                next = R.pass ? rref : PBRS_NONE;
+            }
+            return;
+        }
+        if (lvl) {
+            // shape/src/blas.rs:456-466: near = left iff dir[axis] > 0; the far child is pushed
+            // first and re-tested against the extent of the moment when it is popped
+            bool left_near = comp(d, (int)(meta & 3u)) > 0.0f;
+            const BoxTest &N = left_near ? L : R, &F = left_near ? R : L;
+            if (F.pass) push(left_near ? rref : lref, F.tl, self | (left_near ? 0x80000000u : 0u), dg);
+            next = N.pass ? (left_near ? lref : rref) : PBRS_NONE;
+            return;
+        }
+        // tlas/src/bvh.rs:83-100: left, then right against whatever extent the left subtree leaves
+        if (R.overlap) push(rref, R.tl, self | 0x80000000u, dg);
+        if (L.pass) next = lref;
+        else { next = PBRS_NONE; ret = PB_INF; }
+    }
+
+    // ---- phase 2a: a leaf ----
+    PB_DEV void leaf(const DeviceScene &sc, Diag &dg, TravCount &tc) {
+        const uint32_t first = next & ~PBRS_LEAF_BIT;
+        next = PBRS_NONE;
+        if (lvl) {
+            // a run of triangles (shape/src/blas.rs:447-454): all see the extent of the pop
+            Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
+            uint32_t s = mesh.tri_base + first;
+            while (true) {
+                TriVerts tv = load_tri(sc.tris + s);
+                if (COUNT) tc.tris++;
+                if (ANY) {
+                    if (tri_occludes(tv.p0, tv.p1, tv.p2, ray, dg)) { occluded = true; done = true; return; }
+                } else {
+                    float t;
+                    bool hit;
+                    if (tv.flags & PBRS_TRI_CHECK_SHADING) {
+                        MeshHit mh;
+                        hit = mesh_tri_shade(sc, mesh, tv, ray, mh, dg);
+                        t = mh.t;
+                    } else {
+                        TriHit h;
+                        hit = tri_intersect(tv.p0, tv.p1, tv.p2, ray, h, dg);
+                        t = h.t;
+                    }
+                    if (hit && t < l_best_t) { l_best_t = t; l_best_tri = s; }
+                }
+                if (tv.flags & PBRS_TRI_LAST_IN_LEAF) break;
+                ++s;
+            }
+            if (!ANY) t_max = l_best_t;  // blas.rs:468
+            return;
+        }
+        // an instance (tlas/src/instance.rs:50-72): the ray goes to object space
+        if (COUNT) tc.insts++;
+        Ray wr; wr.o = o; wr.d = d; wr.t_max = t_max;
+        uint32_t kind, index;
+        Ray obj = to_object(sc.inst_trav + first, wr, kind, index);
+        if (!(len2(obj.d) > (ANY ? 1e-6f : 1e-3f))) flag(dg, P_MISC);
+        if (kind == PBRS_SHAPE_SPHERE) {
+            if (COUNT) tc.spheres++;
+            f4 s = ld16(sc.spheres + index);
+            if (ANY) {
+                if (sphere_occludes(mk(s.x, s.y, s.z), s.w, obj)) { occluded = true; done = true; }
+                return;
+            }
+            float t;
+            if (sphere_hit_t(mk(s.x, s.y, s.z), s.w, obj, t)) {
+                ret = t;
+                if (t <= best.t) { best.t = t; best.inst = first; best.tri = 0u; }
+            } else {
+                ret = PB_INF;
+            }
+            return;
+        }
+        // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
+        mesh = load_mesh_head(sc.meshes + index);
+        wo = o; wd = d; w_t_max = t_max;
+        set_space(obj.o, obj.d, obj.t_max);
+        BoxTest rb = test_box(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], o, d, rd, fast, t_max);
+        if (!rb.pass) {
+            set_space(wo, wd, w_t_max);
+            if (!ANY) ret = PB_INF;
+            return;
+        }
+        cur_inst = first;
+        l_best_t = PB_INF; l_best_tri = PBRS_NONE;
+        lvl = 1u;
+        push(PBRS_TAG_EXIT, 0.0f, 0u, dg);
+        if (mesh.root_is_leaf) {
+            next = PBRS_LEAF_BIT;  // its triangles see the incoming extent (the clone of `r`)
+        } else {
+            next = 0u;
+            if (!ANY) t_max = PB_INF;  // Q17: after the root's pop the extent is the walk's own best
+        }
+    }
+
+    // ---- phase 2b: unwind the stack until there is something to visit ----
+    PB_DEV void unwind(const DeviceScene &sc, Diag &dg) {
+        while (true) {
+            if (sp == 0) { done = true; return; }
+            --sp;
+            const uint32_t ref = st_ref[sp];
+            if (lvl) {
+                if (ref == PBRS_TAG_EXIT) {
+                    // the mesh walk is over: back to the world ray
+                    lvl = 0u;
+                    set_space(wo, wd, w_t_max);
+                    if (ANY) continue;
+                    if (l_best_t < PB_INF) {
+                        ret = l_best_t;
+                        if (l_best_t <= best.t) { best.t = l_best_t; best.inst = cur_inst; best.tri = l_best_tri; }
+                    } else {
+                        ret = PB_INF;
+                    }
+                    continue;
+                }
+                if (ANY) { next = ref; return; }
+                int rt = retest(st_tl[sp], t_max);
+                if (rt < 0) rt = exact_child(sc, st_par[sp], t_max) ? 1 : 0;
+                if (rt) { next = ref; return; }
+                continue;
+            }
+            if (ANY) { next = ref; return; }
+            if (ref == PBRS_TAG_COMBINE) {
+                float lv = st_tl[sp];
+                ret = (lv < ret) ? lv : ret;  // pick(l, r).t
+                continue;
+            }
+            // a right child whose left sibling subtree just completed with value `ret`
+            const float r_tl = st_tl[sp];
+            const uint32_t par = st_par[sp];
+            if (ret < PB_INF) {
+                t_max = ret;  // ray.set_extent(isect.ray_t), tlas/src/bvh.rs:85-87
+                st_ref[sp] = PBRS_TAG_COMBINE; st_tl[sp] = ret; ++sp;
+            }
+            int rt = retest(r_tl, t_max);
+            if (rt < 0) rt = exact_child(sc, par, t_max) ? 1 : 0;
+            if (rt) { next = ref; return; }
+            ret = PB_INF;
+        }
+    }
+
+    // one step of phase 2 (call when !at_inner() && !done)
+    PB_DEV void step2(const DeviceScene &sc, Diag &dg, TravCount &tc) {
+        if (next != PBRS_NONE) leaf(sc, dg, tc);
+        if (!done && next == PBRS_NONE) unwind(sc, dg);
+    }
+
+    // the whole walk, sequentially (host-sim and single-ray callers)
+    PB_DEV void run(const DeviceScene &sc, const Ray &ray, Diag &dg, TravCount &tc) {
+        begin(sc, ray);
+        while (!done) {
+            while (at_inner()) expand(sc, dg, tc);
+            if (!done) step2(sc, dg, tc);
+        }
+    }
+};
+
+}  // namespace pbrs

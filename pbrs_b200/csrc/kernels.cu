@@ -70,16 +70,77 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_extend(DeviceScene sc, PathBuffers pb, const uint32_t *queue, const uint32_t *count) {
+// Persistent traversal kernel (closest hit: ANY = false, shadow entries: ANY = true).
+// Every lane owns one Walk; the warp alternates phase 1 (inner-node expansions, all levels) and
+// phase 2 (one leaf or unwind) and, whenever enough lanes have run dry, draws the next rays from
+// the queue with a single atomicAdd on the launch's work cursor.
+constexpr int kRefillIdleLanes = 10;  // refill as soon as this many lanes are idle
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor) {
     Diag dg; dg.panics = 0u;
     TravCount tc; tc.nodes = tc.tris = tc.spheres = tc.insts = 0u;
-    PBRS_WARP_LOOP(*count, i, active) {
-        if (active) stage_extend<COUNT>(sc, pb, queue[i], dg, tc);
+    const uint32_t n = *count;
+    uint32_t st_ref[PBRS_WALK_STACK], st_par[ANY ? 1 : PBRS_WALK_STACK];
+    float st_tl[ANY ? 1 : PBRS_WALK_STACK];
+    Walk<ANY, COUNT> w(st_ref, st_tl, st_par);
+    w.done = true; w.next = PBRS_NONE;
+    bool busy = false, exhausted = false;
+    uint32_t j = 0u, vis = 0u;
+    int which = 0;
+    while (true) {
+        // ---- refill idle lanes ----
+        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= kRefillIdleLanes)) {
+            int leader = __ffs(idle) - 1;
+            uint32_t base = 0u;
+            if ((int)lane_id() == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+            if (!busy) {
+                uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane_id()) - 1u));
+                if (i < n) {
+                    j = queue[i];
+                    busy = true;
+                    if (ANY) {
+                        vis = 0u;
+                        Ray r;
+                        which = 0;
+                        if (!shadow_ray(pb, j, 0, r)) { which = 1; shadow_ray(pb, j, 1, r); }
+                        w.begin(sc, r);
+                    } else {
+                        w.begin(sc, load_ray(pb, j));
+                    }
+                }
+            }
+        } else if (idle == 0xFFFFFFFFu) {
+            break;
+        }
+        // ---- phase 1: inner nodes ----
+        while (busy && w.at_inner()) w.expand(sc, dg, tc);
+        __syncwarp();
+        // ---- phase 2: one leaf / unwind ----
+        if (busy && !w.done) w.step2(sc, dg, tc);
+        if (busy && w.done) {
+            if (ANY) {
+                if (!w.occluded) vis |= 1u << which;
+                Ray r;
+                if (which == 0 && shadow_ray(pb, j, 1, r)) {
+                    which = 1;
+                    w.begin(sc, r);
+                } else {
+                    shadow_finish(pb, j, vis);
+                    busy = false;
+                }
+            } else {
+                store_hit(pb, j, w.best);
+                busy = false;
+            }
+        }
     }
     __syncwarp();
     flush_diag(pb.stats, dg);
-    if (COUNT) flush_count(pb.stats, tc, 0);
+    if (COUNT) flush_count(pb.stats, tc, ANY ? 1 : 0);
 }
 
 __global__ void __launch_bounds__(kThreads) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, const uint32_t *queue,
@@ -104,18 +165,6 @@ __global__ void __launch_bounds__(kThreads) k_shade(DeviceScene sc, PathBuffers 
     __syncwarp();
     warp_add_stat(pb.stats + kStatShadowRays, rays);
     flush_diag(pb.stats, dg);
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_shadow(DeviceScene sc, PathBuffers pb, const uint32_t *count) {
-    Diag dg; dg.panics = 0u;
-    TravCount tc; tc.nodes = tc.tris = tc.spheres = tc.insts = 0u;
-    PBRS_WARP_LOOP(*count, i, active) {
-        if (active) stage_shadow<COUNT>(sc, pb, pb.shadow_queue[i], dg, tc);
-    }
-    __syncwarp();
-    flush_diag(pb.stats, dg);
-    if (COUNT) flush_count(pb.stats, tc, 1);
 }
 
 __global__ void __launch_bounds__(kThreads) k_accumulate(PathBuffers pb, FrameParams fp, BatchParams bp, float *film) {
@@ -216,11 +265,11 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint
         w.sms = prop.multiProcessorCount;
     }
     if (!w.grid_ready) {
-        w.grid.extend = blocks_for(k_extend<false>, w.sms);
-        w.grid.extend_count = blocks_for(k_extend<true>, w.sms);
+        w.grid.extend = blocks_for(k_trace<false, false>, w.sms);
+        w.grid.extend_count = blocks_for(k_trace<false, true>, w.sms);
         w.grid.shade = blocks_for(k_shade, w.sms);
-        w.grid.shadow = blocks_for(k_shadow<false>, w.sms);
-        w.grid.shadow_count = blocks_for(k_shadow<true>, w.sms);
+        w.grid.shadow = blocks_for(k_trace<true, false>, w.sms);
+        w.grid.shadow_count = blocks_for(k_trace<true, true>, w.sms);
         w.grid.small = blocks_for(k_generate, w.sms);
         w.grid_ready = true;
     }
@@ -297,7 +346,7 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     // stages per path: the path integrator's bounce loop, or the direct integrator's two stages
     int n_stages = o.integrator == PBRS_INTEGRATOR_PATH ? std::max(o.max_depth, 0) : (o.max_depth > 0 ? 2 : 0);
     if (tg.only_sample >= 0) n_stages = 1;
-    if (n_stages > PBRS_COUNTS_PER_BATCH / 2 - 1) { set_error("max_depth too large"); return PBRS_ERR_INVALID_ARG; }
+    if (n_stages > PBRS_MAX_STAGES) { set_error("max_depth too large (at most 15 bounces)"); return PBRS_ERR_INVALID_ARG; }
 
     uint32_t capacity = o.paths_in_flight ? o.paths_in_flight : (1u << 22);
     const uint64_t total_pixels = (uint64_t)fp.n_tiles * 4096u;
@@ -354,15 +403,15 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         for (int stage = 0; stage < n_stages; ++stage) {
             uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
             uint32_t *c_in = pb.counts + 2 * stage, *c_shadow = pb.counts + 2 * stage + 1, *c_out = pb.counts + 2 * (stage + 1);
-            if (count_trav) k_extend<true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, c_in);
-            else k_extend<false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, c_in);
+            if (count_trav) k_trace<false, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, c_in, pb.counts + 32 + stage);
+            else k_trace<false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, c_in, pb.counts + 32 + stage);
             ++launches; ++launches_extend;
             mark(T_EXT);
             if (tg.only_sample >= 0) break;
             k_shade<<<w.grid.shade, kThreads, 0, stream>>>(sc, pb, fp, bp, q_in, c_in, q_out, c_out, c_shadow, stage);
             mark(T_SHADE);
-            if (count_trav) k_shadow<true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, c_shadow);
-            else k_shadow<false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, c_shadow);
+            if (count_trav) k_trace<true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, c_shadow, pb.counts + 48 + stage);
+            else k_trace<true, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, c_shadow, pb.counts + 48 + stage);
             mark(T_SHADOW);
             launches += 2; ++launches_shadow;
         }

@@ -319,12 +319,17 @@ def instanced_field(width=3840, height=2160, n_side=100, n_meshes=10, ico_subdiv
 
 
 # name -> (generator, integrator, msaa) : the BASELINE.json configs
+def _wh(w, h, s):
+    return max(2, int(round(w * s))), max(2, int(round(h * s)))
+
+
+# `s` scales the frame (1.0 = the BASELINE.json size); used only to shorten profiling runs
 CONFIGS = {
-    "c1": (lambda: cornell_box(512, 512), "path", 4),
-    "c2": (lambda: cornell_box(1920, 1080), "direct", 1),
-    "c3": (lambda: spheres500(1920, 1080), "path", 8),
-    "c4": (lambda: mesh_terrain(3840, 2160), "path", 16),
-    "c5": (lambda: instanced_field(3840, 2160), "path", 32),
+    "c1": (lambda s=1.0: cornell_box(*_wh(512, 512, s)), "path", 4),
+    "c2": (lambda s=1.0: cornell_box(*_wh(1920, 1080, s)), "direct", 1),
+    "c3": (lambda s=1.0: spheres500(*_wh(1920, 1080, s)), "path", 8),
+    "c4": (lambda s=1.0: mesh_terrain(*_wh(3840, 2160, s)), "path", 16),
+    "c5": (lambda s=1.0: instanced_field(*_wh(3840, 2160, s)), "path", 32),
 }
 WORKLOAD_NAMES = {
     "c1": "C1 cornell-box 512x512 16spp path depth5",

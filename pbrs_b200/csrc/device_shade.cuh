@@ -178,10 +178,18 @@ PB_DEV void specular_refract(const Lobe &l, vec3 wo, vec3 &wi, color &c, Diag &d
     wi = t;
     c = (f_tr / fabsf(cos_theta(t))) * l.albedo;
 }
+// K >= 0: the lobe kind is a compile-time constant (material-class kernels); K < 0: read l.kind.
+// The *_t templates hold the arithmetic; the un-suffixed entry points inline them for a known K
+// and go through one out-of-line generic copy (*_dyn) otherwise.
+template <int K>
+PB_DEV int kind_of(const Lobe &l) { return K >= 0 ? K : l.kind; }
+
 // :458-460, 540-559 (Lambert only: Oren-Nayar is never instantiated by a material), 594-609
-PB_CALL color lobe_eval(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
-    if (l.kind == LOBE_SPECULAR) return blackc();
-    if (l.kind == LOBE_LAMBERT) return l.albedo * kInvPi;
+template <int K>
+PB_DEV color lobe_eval_t(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
+    const int kind = kind_of<K>(l);
+    if (kind == LOBE_SPECULAR) return blackc();
+    if (kind == LOBE_LAMBERT) return l.albedo * kInvPi;
     float cto = fabsf(cos_theta(wo));
     float cti = fabsf(cos_theta(wi));
     vec3 wh;
@@ -192,9 +200,11 @@ PB_CALL color lobe_eval(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
     return l.albedo * mf_d(l.ax, l.ay, wh, dg) * mf_g(l.ax, l.ay, wo, wi) * refl * weak_recip(4.0f * cto * cti);
 }
 // :503-505, 566-572 (Q6), 628-638
-PB_CALL Prob lobe_prob(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
-    if (l.kind == LOBE_SPECULAR) return Mass(0.0f);
-    if (l.kind == LOBE_LAMBERT) {
+template <int K>
+PB_DEV Prob lobe_prob_t(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
+    const int kind = kind_of<K>(l);
+    if (kind == LOBE_SPECULAR) return Mass(0.0f);
+    if (kind == LOBE_LAMBERT) {
         if (wo.z * wi.z >= 0.0f) return Density(wi.z * kInvPi);
         return Density(0.0f);
     }
@@ -204,8 +214,10 @@ PB_CALL Prob lobe_prob(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
     return Density(0.0f);
 }
 // :462-501, 560-564, 611-626
-PB_CALL void lobe_sample(const Lobe &l, vec3 wo, float r0, float r1, color &f, vec3 &wi, Prob &pr, Diag &dg) {
-    if (l.kind == LOBE_SPECULAR) {
+template <int K>
+PB_DEV void lobe_sample_t(const Lobe &l, vec3 wo, float r0, float r1, color &f, vec3 &wi, Prob &pr, Diag &dg) {
+    const int kind = kind_of<K>(l);
+    if (kind == LOBE_SPECULAR) {
         if (l.intrusion == INTR_REFLECTION) {
             specular_reflect(l, wo, wi, f, dg);
             pr = Mass(1.0f);
@@ -219,20 +231,40 @@ PB_CALL void lobe_sample(const Lobe &l, vec3 wo, float r0, float r1, color &f, v
         }
         return;
     }
-    if (l.kind == LOBE_LAMBERT) {
+    if (kind == LOBE_LAMBERT) {
         if (!(cos_theta(wo) >= 0.0f)) flag(dg, P_LAMBERT_WO);
         wi = cos_sample_hemisphere(r0, r1);
-        f = lobe_eval(l, wo, wi, dg);
-        pr = lobe_prob(l, wo, wi, dg);
+        f = lobe_eval_t<LOBE_LAMBERT>(l, wo, wi, dg);
+        pr = lobe_prob_t<LOBE_LAMBERT>(l, wo, wi, dg);
         return;
     }
     vec3 wh = mf_sample_wh(l.ax, l.ay, wo, r0, r1, dg);
     vec3 w = reflect(wh, wo);
     if (!same_hemisphere(wo, w)) { f = blackc(); wi = mk(0.0f, 0.0f, 1.0f); pr = Density(0.0f); return; }
     float pdf = mf_pdf(l.ax, l.ay, wh, dg) / (4.0f * dot(wo, wh));
-    f = lobe_eval(l, wo, w, dg);
+    f = lobe_eval_t<LOBE_MICROFACET>(l, wo, w, dg);
     wi = w;
     pr = Density(pdf);
+}
+PB_CALL color lobe_eval_dyn(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) { return lobe_eval_t<-1>(l, wo, wi, dg); }
+PB_CALL Prob lobe_prob_dyn(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) { return lobe_prob_t<-1>(l, wo, wi, dg); }
+PB_CALL void lobe_sample_dyn(const Lobe &l, vec3 wo, float r0, float r1, color &f, vec3 &wi, Prob &pr, Diag &dg) {
+    lobe_sample_t<-1>(l, wo, r0, r1, f, wi, pr, dg);
+}
+template <int K>
+PB_DEV color lobe_eval(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
+    if constexpr (K < 0) return lobe_eval_dyn(l, wo, wi, dg);
+    else return lobe_eval_t<K>(l, wo, wi, dg);
+}
+template <int K>
+PB_DEV Prob lobe_prob(const Lobe &l, vec3 wo, vec3 wi, Diag &dg) {
+    if constexpr (K < 0) return lobe_prob_dyn(l, wo, wi, dg);
+    else return lobe_prob_t<K>(l, wo, wi, dg);
+}
+template <int K>
+PB_DEV void lobe_sample(const Lobe &l, vec3 wo, float r0, float r1, color &f, vec3 &wi, Prob &pr, Diag &dg) {
+    if constexpr (K < 0) lobe_sample_dyn(l, wo, r0, r1, f, wi, pr, dg);
+    else lobe_sample_t<K>(l, wo, r0, r1, f, wi, pr, dg);
 }
 
 // ---- textures: texture/src/lib.rs ----
@@ -314,40 +346,50 @@ PB_DEV Lobe mk_microfacet(color albedo, float ax, float ay) {
 PB_DEV color mtl_emission(const MaterialRec &m) {  // :291-299
     return m.kind == PBRS_MTL_DIFFUSE_LIGHT ? mkc(m.a[0], m.a[1], m.a[2]) : blackc();
 }
-PB_CALL void bxdfs_at(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
+// CLS: the material class the caller is specialised for (PBRS_CLS_ANY: none); only the material
+// kinds of that class are compiled in.
+PB_DEV constexpr bool cls_has(int cls, int kind) {
+    return cls == PBRS_CLS_ANY ||
+           (cls == PBRS_CLS_LAMBERT && (kind == PBRS_MTL_LAMBERTIAN || kind == PBRS_MTL_SUBSTRATE)) ||
+           (cls == PBRS_CLS_MICROFACET && (kind == PBRS_MTL_METAL || kind == PBRS_MTL_GLOSSY)) ||
+           (cls == PBRS_CLS_SPECULAR && (kind == PBRS_MTL_MIRROR || kind == PBRS_MTL_DIELECTRIC)) ||
+           (cls == PBRS_CLS_MULTI && (kind == PBRS_MTL_PLASTIC || kind == PBRS_MTL_UBER));
+}
+// the lobe kind every lobe of a class has, or -1
+PB_DEV constexpr int cls_lobe_kind(int cls) {
+    return cls == PBRS_CLS_LAMBERT ? LOBE_LAMBERT : cls == PBRS_CLS_MICROFACET ? LOBE_MICROFACET : cls == PBRS_CLS_SPECULAR ? LOBE_SPECULAR
+           : cls == PBRS_CLS_EMISSIVE ? LOBE_LAMBERT /* no lobes at all */ : -1;
+}
+template <int CLS>
+PB_DEV void bxdfs_at_t(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
     L.n = 0;
     color ca = mkc(m.a[0], m.a[1], m.a[2]), cb = mkc(m.b[0], m.b[1], m.b[2]);
-    switch (m.kind) {
-    case PBRS_MTL_LAMBERTIAN:  // :180-184
+    if (cls_has(CLS, PBRS_MTL_LAMBERTIAN) && m.kind == PBRS_MTL_LAMBERTIAN) {  // :180-184
         L.l[L.n++] = mk_lambert(texture_value(sc, m.tex_kd, h.u, h.v, h.pos, dg));
-        break;
-    case PBRS_MTL_METAL: {  // :200-206
+    }
+    if (cls_has(CLS, PBRS_MTL_METAL) && m.kind == PBRS_MTL_METAL) {  // :200-206
         float alpha = roughness_to_alpha(m.f[0]);
         Lobe l = mk_microfacet(grayc(1.0f), alpha, alpha);
         l.fresnel = FR_CONDUCTOR; l.eta_t = ca; l.k = cb;
         L.l[L.n++] = l;
-        break;
     }
-    case PBRS_MTL_GLOSSY: {  // :72-78, :216-218
+    if (cls_has(CLS, PBRS_MTL_GLOSSY) && m.kind == PBRS_MTL_GLOSSY) {  // :72-78, :216-218
         float alpha = roughness_to_alpha(m.f[0]);
         L.l[L.n++] = mk_microfacet(ca, alpha, alpha);
-        break;
     }
-    case PBRS_MTL_MIRROR:  // :229-232
+    if (cls_has(CLS, PBRS_MTL_MIRROR) && m.kind == PBRS_MTL_MIRROR) {  // :229-232
         L.l[L.n++] = mk_specular(ca, INTR_REFLECTION, FR_NOP, 0.0f, 0.0f);
-        break;
-    case PBRS_MTL_DIELECTRIC:  // :265-268
+    }
+    if (cls_has(CLS, PBRS_MTL_DIELECTRIC) && m.kind == PBRS_MTL_DIELECTRIC) {  // :265-268
         L.l[L.n++] = mk_specular(ca, INTR_HYBRID, FR_DIELECTRIC, 1.0f, m.f[0]);
-        break;
-    case PBRS_MTL_DIFFUSE_LIGHT:  // :291-293
-        break;
-    case PBRS_MTL_PLASTIC: {  // :433-445
+    }
+    // DiffuseLight (:291-293): no lobes
+    if (cls_has(CLS, PBRS_MTL_PLASTIC) && m.kind == PBRS_MTL_PLASTIC) {  // :433-445
         float alpha = m.remap ? roughness_to_alpha(m.f[0]) : m.f[0];
         L.l[L.n++] = mk_microfacet(cb, alpha, alpha);
         L.l[L.n++] = mk_lambert(ca);
-        break;
     }
-    case PBRS_MTL_UBER: {  // :317-365
+    if (cls_has(CLS, PBRS_MTL_UBER) && m.kind == PBRS_MTL_UBER) {  // :317-365
         color transmission = grayc(clampf(1.0f - m.f[3], 0.0f, 1.0f));
         if (!is_black(transmission)) L.l[L.n++] = mk_specular(transmission, INTR_TRANSMISSION, FR_DIELECTRIC, 1.0f, m.f[2]);
         color kd = texture_value(sc, m.tex_kd, h.u, h.v, h.pos, dg);
@@ -368,15 +410,18 @@ PB_CALL void bxdfs_at(const DeviceScene &sc, const MaterialRec &m, const Isect &
             color kt = texture_value(sc, m.tex_kt, h.u, h.v, h.pos, dg);
             if (!is_black(kt)) L.l[L.n++] = mk_specular(kt, INTR_TRANSMISSION, FR_DIELECTRIC, 1.0f, m.f[2]);
         }
-        break;
     }
-    case PBRS_MTL_SUBSTRATE: {  // :393-420 (FresnelBlend is commented out upstream: Lambert only)
+    if (cls_has(CLS, PBRS_MTL_SUBSTRATE) && m.kind == PBRS_MTL_SUBSTRATE) {  // :393-420 (FresnelBlend is commented out upstream: Lambert only)
         color d = texture_value(sc, m.tex_kd, h.u, h.v, h.pos, dg), s = texture_value(sc, m.tex_ks, h.u, h.v, h.pos, dg);
         if (!(is_black(d) && is_black(s))) L.l[L.n++] = mk_lambert(d);
-        break;
     }
-    default: break;
-    }
+}
+
+PB_CALL void bxdfs_at_dyn(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) { bxdfs_at_t<PBRS_CLS_ANY>(sc, m, h, L, dg); }
+template <int CLS>
+PB_DEV void bxdfs_at(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
+    if constexpr (CLS == PBRS_CLS_ANY || CLS == PBRS_CLS_MULTI) bxdfs_at_dyn(sc, m, h, L, dg);
+    else bxdfs_at_t<CLS>(sc, m, h, L, dg);
 }
 
 // ---- BSDF: src/bsdf.rs ----
@@ -396,28 +441,31 @@ PB_DEV Frame bsdf_frame(const Isect &h, Diag &dg) {  // :18-31, :125-137
 }
 PB_DEV vec3 to_local(const Frame &f, vec3 w, Diag &dg) { return hat(mk(dot(f.t, w), dot(f.b, w), dot(f.n, w)), dg); }  // :113-117
 PB_DEV vec3 to_world(const Frame &f, vec3 l) { return l.x * f.t + l.y * f.b + l.z * f.n; }                           // :119-123
-PB_CALL color bsdf_eval(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :43-51
+template <int K>
+PB_DEV color bsdf_eval_t(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :43-51
     vec3 wi = to_local(fr, wi_w, dg);
     vec3 wo = to_local(fr, wo_w, dg);
     if (wo.z == 0.0f) return blackc();
     color s = blackc();
-    for (int i = 0; i < L.n; ++i) s = s + lobe_eval(L.l[i], wo, wi, dg);
+    for (int i = 0; i < L.n; ++i) s = s + lobe_eval<K>(L.l[i], wo, wi, dg);
     return s;
 }
-PB_CALL float bsdf_pdf(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :53-57 (Q4: a sum)
+template <int K>
+PB_DEV float bsdf_pdf_t(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {  // :53-57 (Q4: a sum)
     vec3 wi = to_local(fr, wi_w, dg);
     vec3 wo = to_local(fr, wo_w, dg);
     float s = 0.0f;
     for (int i = 0; i < L.n; ++i) {
-        Prob p = lobe_prob(L.l[i], wo, wi, dg);
+        Prob p = lobe_prob<K>(L.l[i], wo, wi, dg);
         s += p.is_mass ? 0.0f : p.v;
     }
     return s;
 }
 // :59-103.  The chosen lobe is swap_remove()d from the list: the rest are visited with the last
 // lobe moved into the chosen slot.
-PB_CALL void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr,
-                        Diag &dg) {
+template <int K>
+PB_DEV void bsdf_sample_t(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr,
+                          Diag &dg) {
     if (!(u < 1.0f)) flag(dg, P_MISC);
     vec3 wo = to_local(fr, wo_world, dg);
     int n = L.n;
@@ -429,7 +477,7 @@ PB_CALL void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u
     color value;
     vec3 wi;
     Prob prob;
-    lobe_sample(L.l[chosen], wo, v, remapped_u, value, wi, prob, dg);  // Q2: (v, remapped_u)
+    lobe_sample<K>(L.l[chosen], wo, v, remapped_u, value, wi, prob, dg);  // Q2: (v, remapped_u)
     if (prob.is_mass) { f = value; wi_out = to_world(fr, wi); pr = prob; return; }
     int count = 0;
     float other_sum = 0.0f;
@@ -439,10 +487,10 @@ PB_CALL void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u
         for (int k = 0; k < n - 1; ++k) {
             int src = (k == chosen) ? n - 1 : k;
             if (pass == 0) {
-                Prob p = lobe_prob(L.l[src], wo, wi, dg);
+                Prob p = lobe_prob<K>(L.l[src], wo, wi, dg);
                 if (!p.is_mass) { count++; other_sum += p.v; }
             } else {
-                others = others + lobe_eval(L.l[src], wo, wi, dg);
+                others = others + lobe_eval<K>(L.l[src], wo, wi, dg);
             }
         }
     float overall = (prob.v + other_sum) / (float)(1 + count);
@@ -450,13 +498,35 @@ PB_CALL void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u
     wi_out = to_world(fr, wi);
     pr = Density(overall);
 }
+PB_CALL color bsdf_eval_dyn(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) { return bsdf_eval_t<-1>(fr, L, wo_w, wi_w, dg); }
+PB_CALL float bsdf_pdf_dyn(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) { return bsdf_pdf_t<-1>(fr, L, wo_w, wi_w, dg); }
+PB_CALL void bsdf_sample_dyn(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr, Diag &dg) {
+    bsdf_sample_t<-1>(fr, L, wo_world, u, v, f, wi_out, pr, dg);
+}
+template <int K>
+PB_DEV color bsdf_eval(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {
+    if constexpr (K < 0) return bsdf_eval_dyn(fr, L, wo_w, wi_w, dg);
+    else return bsdf_eval_t<K>(fr, L, wo_w, wi_w, dg);
+}
+template <int K>
+PB_DEV float bsdf_pdf(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) {
+    if constexpr (K < 0) return bsdf_pdf_dyn(fr, L, wo_w, wi_w, dg);
+    else return bsdf_pdf_t<K>(fr, L, wo_w, wi_w, dg);
+}
+template <int K>
+PB_DEV void bsdf_sample(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr, Diag &dg) {
+    if constexpr (K < 0) bsdf_sample_dyn(fr, L, wo_world, u, v, f, wi_out, pr, dg);
+    else bsdf_sample_t<K>(fr, L, wo_world, u, v, f, wi_out, pr, dg);
+}
 // :104-112
+template <int K>
 PB_DEV bool bsdf_sample_specular(const Frame &fr, const Lobes &L, vec3 wo_world, color &f, vec3 &wi_out, Prob &pr, Diag &dg) {
+    if constexpr (K >= 0 && K != LOBE_SPECULAR) return false;
     vec3 wo = to_local(fr, wo_world, dg);
     for (int i = 0; i < L.n; ++i)
-        if (L.l[i].kind == LOBE_SPECULAR) {
+        if (kind_of<K>(L.l[i]) == LOBE_SPECULAR) {
             vec3 wi;
-            lobe_sample(L.l[i], wo, 0.0f, 0.0f, f, wi, pr, dg);
+            lobe_sample<K>(L.l[i], wo, 0.0f, 0.0f, f, wi, pr, dg);
             wi_out = to_world(fr, wi);
             return true;
         }

@@ -33,16 +33,22 @@ struct PathBuffers {
     f4 *sh_c;   // c1.g, c1.b, c2.g, c2.b
     f4 *sh_b;   // multiplier rgb (path: beta before the bounce; specular stage: f), 1/light_pdf
     float *sh_m;  // < 0: path mode (rad += beta * X); >= 0: specular stage (rad += (X * f) * m)
-    uint32_t *queue[2];
+    uint32_t *queue[2];            // extend queues (ping-pong between bounces)
+    uint32_t *cls_queue[PBRS_NUM_CLS];  // shade queues, one per material class, filled by the extend kernel
     uint32_t *shadow_queue;
-    uint32_t *counts;              // this batch's counter block (see kCount*)
+    uint32_t *counts;              // this batch's counter block (see PBRS_CNT_*)
     unsigned long long *stats;     // kStat* accumulators of the whole call
     uint32_t capacity;
 };
-// counter block layout, per batch: [2*b] extend-queue length of bounce b, [2*b+1] shadow-queue length,
-// [32+b] / [48+b] the work cursors the persistent extend / shadow kernels of bounce b draw rays from
-#define PBRS_COUNTS_PER_BATCH 64
+// counter block layout: per batch, 16 words per stage
 #define PBRS_MAX_STAGES 15
+#define PBRS_CNT_STRIDE 16
+#define PBRS_COUNTS_PER_BATCH (PBRS_CNT_STRIDE * (PBRS_MAX_STAGES + 1))
+#define PBRS_CNT_EXTEND 0         // extend-queue length of the stage
+#define PBRS_CNT_SHADOW 1         // shadow-queue length
+#define PBRS_CNT_EXTEND_CURSOR 2  // work cursors the persistent extend / shadow kernels draw rays from
+#define PBRS_CNT_SHADOW_CURSOR 3
+#define PBRS_CNT_CLS 4            // [4 .. 4+PBRS_NUM_CLS): shade-queue lengths per material class
 // [kStatTrav + 4*k + {0..3}] = nodes, tris, spheres, instances of the closest-hit (k=0) / any-hit (k=1) walks
 enum { kStatShadowRays = 0, kStatTrav = 1, kStatPanic0 = 12, kStatCount = 28 };
 
@@ -163,6 +169,11 @@ PB_DEV void store_hit(const PathBuffers &pb, uint32_t j, const Hit &h) {
     pb.hit[j] = rec;
 #endif
 }
+// which shade queue a finished closest-hit walk joins
+PB_DEV uint32_t hit_class(const DeviceScene &sc, const Hit &h) {
+    if (h.inst == PBRS_NONE) return PBRS_CLS_MISS;
+    return ld_u32(&sc.inst_shade[h.inst].cls);
+}
 template <bool COUNT>
 PB_DEV void stage_extend(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
     uint32_t st_ref[PBRS_WALK_STACK], st_par[PBRS_WALK_STACK];
@@ -223,8 +234,9 @@ PB_DEV float power_heuristic2(float nf, float f_pdf, float ng, float g_pdf) {  /
     float f = nf * f_pdf, g = ng * g_pdf;
     return (f * f) / (f * f + g * g);
 }
-PB_CALL int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
-                            ShadowOut &so, Diag &dg) {
+template <int K>
+PB_DEV int sample_one_light_t(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
+                              ShadowOut &so, Diag &dg) {
     so.has1 = so.has2 = false;
     uint32_t nd = sc.n_delta, na = sc.n_area;
     uint32_t n = nd + na + sc.has_env;
@@ -256,9 +268,9 @@ PB_CALL int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobe
             lr = mkc(lt.color[0], lt.color[1], lt.color[2]);
             wi = -cd;
         }
-        color bsdf_value = bsdf_eval(fr, L, hit.wo, wi, dg) * fabsf(dot(hit.normal, wi));
+        color bsdf_value = bsdf_eval<K>(fr, L, hit.wo, wi, dg) * fabsf(dot(hit.normal, wi));
         if (is_black(lr) || is_black(bsdf_value)) return 0;
-        (void)bsdf_pdf(fr, L, hit.wo, wi, dg);
+        (void)bsdf_pdf<K>(fr, L, hit.wo, wi, dg);
         so.r1 = vis;
         so.c1 = bsdf_value * lr * 1.0f * weak_recip(1.0f);
         so.has1 = true;
@@ -277,8 +289,8 @@ PB_CALL int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobe
             if (!area_shape_pdf_at(lt, hit, wi, pdf, dg)) pdf = 0.0f;
             Ray vis = spawn_limited_ray_to(hit, pol_pos);
             if (pdf > 0.0f && !is_black(lr)) {
-                color bsdf_value = bsdf_eval(fr, L, hit.wo, wi, dg) * fabsf(dot(hit.normal, wi));
-                float scatter_pdf = bsdf_pdf(fr, L, hit.wo, wi, dg);
+                color bsdf_value = bsdf_eval<K>(fr, L, hit.wo, wi, dg) * fabsf(dot(hit.normal, wi));
+                float scatter_pdf = bsdf_pdf<K>(fr, L, hit.wo, wi, dg);
                 if (!is_black(bsdf_value) && scatter_pdf > 0.0f) {
                     float weight = power_heuristic2(1.0f, pdf, 1.0f, scatter_pdf);
                     so.r1 = vis;
@@ -292,7 +304,7 @@ PB_CALL int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobe
             color bv;
             vec3 wi2;
             Prob bp;
-            bsdf_sample(fr, L, hit.wo, s0, s1, bv, wi2, bp, dg);
+            bsdf_sample<K>(fr, L, hit.wo, s0, s1, bv, wi2, bp, dg);
             bv = bv * fabsf(dot(hit.normal, wi2));
             if (!(is_black(bv) || !(bp.v > 0.0f))) {
                 // DiffuseAreaLight::radiance_to, light/src/lib.rs:141-146
@@ -317,12 +329,23 @@ PB_CALL int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobe
     color f;
     vec3 wi;
     Prob pr;
-    bsdf_sample(fr, L, hit.wo, s0, s1, f, wi, pr, dg);
+    bsdf_sample<K>(fr, L, hit.wo, s0, s1, f, wi, pr, dg);
     Ray incident = spawn_ray(hit, wi);
     so.r1 = incident;
     so.c1 = eval_env(sc, incident.d, dg) * f * fabsf(dot(wi, hit.normal)) * weak_recip(pr.v);
     so.has1 = true;
     return 1;
+}
+
+PB_CALL int sample_one_light_dyn(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
+                                ShadowOut &so, Diag &dg) {
+    return sample_one_light_t<-1>(sc, hit, L, fr, smp, base, so, dg);
+}
+template <int K>
+PB_DEV int sample_one_light(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
+                            ShadowOut &so, Diag &dg) {
+    if constexpr (K < 0) return sample_one_light_dyn(sc, hit, L, fr, smp, base, so, dg);
+    else return sample_one_light_t<K>(sc, hit, L, fr, smp, base, so, dg);
 }
 
 PB_DEV void store_shadow(const PathBuffers &pb, uint32_t j, const ShadowOut &so, color mult, float mode) {
@@ -343,8 +366,10 @@ struct ShadeOut {
 // ---------------------------------------------------------------------------------------------
 // shade, path integrator: the body of the bounce loop, src/pathintegrator.rs:14-73
 // ---------------------------------------------------------------------------------------------
+template <int CLS>
 PB_DEV ShadeOut stage_shade_path(const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j,
                                  int bounce, Diag &dg) {
+    constexpr int K = cls_lobe_kind(CLS);
     ShadeOut out;
     out.next = false; out.shadow_rays = 0;
     Ray ray = load_ray(pb, j);
@@ -354,7 +379,7 @@ PB_DEV ShadeOut stage_shade_path(const DeviceScene &sc, const PathBuffers &pb, c
 #else
     hr = pb.hit[j];
 #endif
-    bool hit = hr.y != 0xFFFFFFFFu;
+    const bool hit = CLS == PBRS_CLS_ANY ? hr.y != 0xFFFFFFFFu : CLS != PBRS_CLS_MISS;
     f4 bt = load_f4(pb.beta + j), rd = load_f4(pb.rad + j);
     color beta = mkc(bt.x, bt.y, bt.z), radiance = mkc(rd.x, rd.y, rd.z);
     bool specular_bounce = (f2u(bt.w) & 1u) != 0u;
@@ -374,16 +399,16 @@ PB_DEV ShadeOut stage_shade_path(const DeviceScene &sc, const PathBuffers &pb, c
     }
     const MaterialRec &m = sc.materials[mtl_id];
     Lobes L;
-    bxdfs_at(sc, m, h, L, dg);  // :31
+    bxdfs_at<CLS>(sc, m, h, L, dg);  // :31
     Frame fr = bsdf_frame(h, dg);
     ShadowOut so;
-    out.shadow_rays = sample_one_light(sc, h, L, fr, smp, base, so, dg);  // :35
+    out.shadow_rays = sample_one_light<K>(sc, h, L, fr, smp, base, so, dg);  // :35
     if (out.shadow_rays > 0) store_shadow(pb, j, so, beta, -1.0f);
     float r0 = smp.f(base + 5), r1 = smp.f(base + 6);  // :46
     color f;
     vec3 wi;
     Prob pr;
-    bsdf_sample(fr, L, -ray.d, r0, r1, f, wi, pr, dg);  // :47
+    bsdf_sample<K>(fr, L, -ray.d, r0, r1, f, wi, pr, dg);  // :47
     store_f4(pb.rad + j, radiance.r, radiance.g, radiance.b, 0.0f);
     if (is_black(f) || pr.v == 0.0f) return out;  // :48
     specular_bounce = pr.is_mass;                  // :55
@@ -406,8 +431,10 @@ PB_DEV ShadeOut stage_shade_path(const DeviceScene &sc, const PathBuffers &pb, c
 // shade, direct-lighting integrator: src/directlighting.rs:14-56.  Stage 0 is the primary hit,
 // stage 1 the single specular bounce evaluated by direct_lighting_debug_integrator.
 // ---------------------------------------------------------------------------------------------
+template <int CLS>
 PB_DEV ShadeOut stage_shade_direct(const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j,
                                    int stage, Diag &dg) {
+    constexpr int K = cls_lobe_kind(CLS);
     ShadeOut out;
     out.next = false; out.shadow_rays = 0;
     Ray ray = load_ray(pb, j);
@@ -417,7 +444,7 @@ PB_DEV ShadeOut stage_shade_direct(const DeviceScene &sc, const PathBuffers &pb,
 #else
     hr = pb.hit[j];
 #endif
-    bool hit = hr.y != 0xFFFFFFFFu;
+    const bool hit = CLS == PBRS_CLS_ANY ? hr.y != 0xFFFFFFFFu : CLS != PBRS_CLS_MISS;
     f4 rd = load_f4(pb.rad + j);
     color radiance = mkc(rd.x, rd.y, rd.z);
     Sampler smp = make_sampler(fp, decode_path(fp, bp, j));
@@ -437,15 +464,15 @@ PB_DEV ShadeOut stage_shade_direct(const DeviceScene &sc, const PathBuffers &pb,
             return out;
         }
         Lobes L;
-        bxdfs_at(sc, m, h, L, dg);
+        bxdfs_at<CLS>(sc, m, h, L, dg);
         Frame fr = bsdf_frame(h, dg);
         ShadowOut so;
-        out.shadow_rays = sample_one_light(sc, h, L, fr, smp, 2u, so, dg);
+        out.shadow_rays = sample_one_light<K>(sc, h, L, fr, smp, 2u, so, dg);
         if (out.shadow_rays > 0) store_shadow(pb, j, so, grayc(1.0f), -1.0f);
         color f;
         vec3 wi;
         Prob pr;
-        if (bsdf_sample_specular(fr, L, h.wo, f, wi, pr, dg)) {
+        if (bsdf_sample_specular<K>(fr, L, h.wo, f, wi, pr, dg)) {
             Ray refl = spawn_ray(h, wi);
             store_f4(pb.ray_o + j, refl.o.x, refl.o.y, refl.o.z, refl.t_max);
             store_f4(pb.ray_d + j, refl.d.x, refl.d.y, refl.d.z, 0.0f);
@@ -467,10 +494,10 @@ PB_DEV ShadeOut stage_shade_direct(const DeviceScene &sc, const PathBuffers &pb,
     reconstruct_hit(sc, ray, hr.y, hr.z, h, mtl_id, dg);
     const MaterialRec &m = sc.materials[mtl_id];
     Lobes L;
-    bxdfs_at(sc, m, h, L, dg);
+    bxdfs_at<CLS>(sc, m, h, L, dg);
     Frame fr = bsdf_frame(h, dg);
     ShadowOut so;
-    out.shadow_rays = sample_one_light(sc, h, L, fr, smp, 10u, so, dg);
+    out.shadow_rays = sample_one_light<K>(sc, h, L, fr, smp, 10u, so, dg);
     if (out.shadow_rays > 0) store_shadow(pb, j, so, f, ax.w);
     return out;
 }

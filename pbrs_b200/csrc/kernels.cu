@@ -76,8 +76,11 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 // the queue with a single atomicAdd on the launch's work cursor.
 constexpr int kRefillIdleLanes = 10;  // refill as soon as this many lanes are idle
 
+// `cnt` = this stage's counter block (PBRS_CNT_*).
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, const uint32_t *count, uint32_t *cursor) {
+__global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
+    const uint32_t *count = cnt + (ANY ? PBRS_CNT_SHADOW : PBRS_CNT_EXTEND);
+    uint32_t *cursor = cnt + (ANY ? PBRS_CNT_SHADOW_CURSOR : PBRS_CNT_EXTEND_CURSOR);
     Diag dg; dg.panics = 0u;
     TravCount tc; tc.nodes = tc.tris = tc.spheres = tc.insts = 0u;
     const uint32_t n = *count;
@@ -121,8 +124,8 @@ __global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers 
         __syncwarp();
         // ---- phase 2: one leaf / unwind ----
         if (busy && !w.done) w.step2(sc, dg, tc);
-        if (busy && w.done) {
-            if (ANY) {
+        if (ANY) {
+            if (busy && w.done) {
                 if (!w.occluded) vis |= 1u << which;
                 Ray r;
                 if (which == 0 && shadow_ray(pb, j, 1, r)) {
@@ -132,8 +135,21 @@ __global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers 
                     shadow_finish(pb, j, vis);
                     busy = false;
                 }
-            } else {
+            }
+        } else {
+            // a finished walk: hit record out, path into the shade queue of its material class
+            // (lanes of one class share one atomicAdd)
+            const bool fin = busy && w.done;
+            const unsigned fmask = __ballot_sync(0xFFFFFFFFu, fin);
+            if (fin) {
                 store_hit(pb, j, w.best);
+                const uint32_t cls = hit_class(sc, w.best);
+                const unsigned peers = __match_any_sync(fmask, cls);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0u;
+                if ((int)lane_id() == leader) base = atomicAdd(cnt + PBRS_CNT_CLS + cls, (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                pb.cls_queue[cls][base + (uint32_t)__popc(peers & ((1u << lane_id()) - 1u))] = j;
                 busy = false;
             }
         }
@@ -143,18 +159,23 @@ __global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers 
     if (COUNT) flush_count(pb.stats, tc, ANY ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(kThreads) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, const uint32_t *queue,
-                                                    const uint32_t *count, uint32_t *next_queue, uint32_t *next_count, uint32_t *shadow_count,
-                                                    int bounce) {
+// One shade kernel per material class CLS (its queue was filled by the extend kernel) and
+// integrator: only the code of that class's lobes is compiled in, and the lanes of a warp run
+// the same material code.  `cnt` / `next_cnt` = counter blocks of this stage / the next one.
+template <int CLS, int INTEGRATOR>
+__global__ void __launch_bounds__(kThreads) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
+                                                    uint32_t *next_queue, uint32_t *next_cnt, int bounce) {
     Diag dg; dg.panics = 0u;
     uint32_t rays = 0u;
-    PBRS_WARP_LOOP(*count, i, active) {
+    const uint32_t *queue = pb.cls_queue[CLS];
+    uint32_t *next_count = next_cnt + PBRS_CNT_EXTEND, *shadow_count = cnt + PBRS_CNT_SHADOW;
+    PBRS_WARP_LOOP(cnt[PBRS_CNT_CLS + CLS], i, active) {
         ShadeOut so; so.next = false; so.shadow_rays = 0;
         uint32_t j = 0u;
         if (active) {
             j = queue[i];
-            so = fp.integrator == PBRS_INTEGRATOR_PATH ? stage_shade_path(sc, pb, fp, bp, j, bounce, dg)
-                                                       : stage_shade_direct(sc, pb, fp, bp, j, bounce, dg);
+            so = INTEGRATOR == PBRS_INTEGRATOR_PATH ? stage_shade_path<CLS>(sc, pb, fp, bp, j, bounce, dg)
+                                                    : stage_shade_direct<CLS>(sc, pb, fp, bp, j, bounce, dg);
         }
         uint32_t s1 = warp_push(next_count, so.next);
         if (so.next) next_queue[s1] = j;
@@ -205,8 +226,23 @@ __global__ void __launch_bounds__(kThreads) k_write_samples(PathBuffers pb, Fram
 }
 
 struct Grid {
-    int extend, extend_count, shade, shadow, shadow_count, small;
+    int extend, extend_count, shadow, shadow_count, small;
+    int shade[2][PBRS_NUM_CLS];
 };
+
+template <int INTEGRATOR>
+void launch_shade(const Grid &g, cudaStream_t stream, const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp,
+                  uint32_t *cnt, uint32_t *next_queue, uint32_t *next_cnt, int stage) {
+    const int *gs = g.shade[INTEGRATOR];
+    k_shade<PBRS_CLS_MISS, INTEGRATOR><<<gs[PBRS_CLS_MISS], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    k_shade<PBRS_CLS_EMISSIVE, INTEGRATOR><<<gs[PBRS_CLS_EMISSIVE], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    k_shade<PBRS_CLS_LAMBERT, INTEGRATOR><<<gs[PBRS_CLS_LAMBERT], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    k_shade<PBRS_CLS_MICROFACET, INTEGRATOR><<<gs[PBRS_CLS_MICROFACET], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    k_shade<PBRS_CLS_SPECULAR, INTEGRATOR><<<gs[PBRS_CLS_SPECULAR], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    k_shade<PBRS_CLS_MULTI, INTEGRATOR><<<gs[PBRS_CLS_MULTI], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+}
+template <int INTEGRATOR>
+void size_shade(Grid &g, int sms);
 
 #define CK(call)                                                                                        \
     do {                                                                                                \
@@ -222,6 +258,16 @@ int blocks_for(K kernel, int sms) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     return sms * per_sm;
+}
+template <int INTEGRATOR>
+void size_shade(Grid &g, int sms) {
+    int *gs = g.shade[INTEGRATOR];
+    gs[PBRS_CLS_MISS] = blocks_for(k_shade<PBRS_CLS_MISS, INTEGRATOR>, sms);
+    gs[PBRS_CLS_EMISSIVE] = blocks_for(k_shade<PBRS_CLS_EMISSIVE, INTEGRATOR>, sms);
+    gs[PBRS_CLS_LAMBERT] = blocks_for(k_shade<PBRS_CLS_LAMBERT, INTEGRATOR>, sms);
+    gs[PBRS_CLS_MICROFACET] = blocks_for(k_shade<PBRS_CLS_MICROFACET, INTEGRATOR>, sms);
+    gs[PBRS_CLS_SPECULAR] = blocks_for(k_shade<PBRS_CLS_SPECULAR, INTEGRATOR>, sms);
+    gs[PBRS_CLS_MULTI] = blocks_for(k_shade<PBRS_CLS_MULTI, INTEGRATOR>, sms);
 }
 
 }  // namespace
@@ -267,7 +313,8 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint
     if (!w.grid_ready) {
         w.grid.extend = blocks_for(k_trace<false, false>, w.sms);
         w.grid.extend_count = blocks_for(k_trace<false, true>, w.sms);
-        w.grid.shade = blocks_for(k_shade, w.sms);
+        size_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, w.sms);
+        size_shade<PBRS_INTEGRATOR_PATH>(w.grid, w.sms);
         w.grid.shadow = blocks_for(k_trace<true, false>, w.sms);
         w.grid.shadow_count = blocks_for(k_trace<true, true>, w.sms);
         w.grid.small = blocks_for(k_generate, w.sms);
@@ -277,8 +324,8 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint
     if (!w.stats) CK(cudaMalloc(&w.stats, sizeof(unsigned long long) * kStatCount));
     if (w.capacity < capacity) {
         if (w.slab) { cudaFree(w.slab); w.slab = nullptr; }
-        // 13 x 16-byte arrays + 1 float + 3 queues per path slot
-        size_t per = 13 * sizeof(f4) + sizeof(float) + 3 * sizeof(uint32_t);
+        // 13 x 16-byte arrays + 1 float + (3 + PBRS_NUM_CLS) queues per path slot
+        size_t per = 13 * sizeof(f4) + sizeof(float) + (3 + PBRS_NUM_CLS) * sizeof(uint32_t);
         size_t bytes = per * (size_t)capacity + 4096;
         cudaError_t e = cudaMalloc(&w.slab, bytes);
         if (e != cudaSuccess) { set_error("path workspace: out of device memory"); w.capacity = 0; return PBRS_ERR_OOM; }
@@ -294,6 +341,7 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint
         (void)take(16);  // spare
         pb.sh_m = (float *)take(4);
         pb.queue[0] = (uint32_t *)take(4); pb.queue[1] = (uint32_t *)take(4); pb.shadow_queue = (uint32_t *)take(4);
+        for (int c = 0; c < PBRS_NUM_CLS; ++c) pb.cls_queue[c] = (uint32_t *)take(4);
         pb.capacity = capacity;
     }
     if (w.counts_cap < n_batches) {
@@ -397,23 +445,24 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         bp.n_pixels = (uint32_t)std::min<uint64_t>(ppb, total_pixels - (uint64_t)b * ppb);
         bp.n_paths = bp.n_pixels * fp.spp_r;
         pb.counts = w.counts + (size_t)b * PBRS_COUNTS_PER_BATCH;
-        k_generate<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, pb.counts + 0);
+        k_generate<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, pb.counts + PBRS_CNT_EXTEND);
         ++launches;
         mark(T_GEN);
         for (int stage = 0; stage < n_stages; ++stage) {
             uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
-            uint32_t *c_in = pb.counts + 2 * stage, *c_shadow = pb.counts + 2 * stage + 1, *c_out = pb.counts + 2 * (stage + 1);
-            if (count_trav) k_trace<false, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, c_in, pb.counts + 32 + stage);
-            else k_trace<false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, c_in, pb.counts + 32 + stage);
+            uint32_t *cnt = pb.counts + PBRS_CNT_STRIDE * stage, *next_cnt = cnt + PBRS_CNT_STRIDE;
+            if (count_trav) k_trace<false, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+            else k_trace<false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
             ++launches; ++launches_extend;
             mark(T_EXT);
             if (tg.only_sample >= 0) break;
-            k_shade<<<w.grid.shade, kThreads, 0, stream>>>(sc, pb, fp, bp, q_in, c_in, q_out, c_out, c_shadow, stage);
+            if (o.integrator == PBRS_INTEGRATOR_PATH) launch_shade<PBRS_INTEGRATOR_PATH>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
+            else launch_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
             mark(T_SHADE);
-            if (count_trav) k_trace<true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, c_shadow, pb.counts + 48 + stage);
-            else k_trace<true, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, c_shadow, pb.counts + 48 + stage);
+            if (count_trav) k_trace<true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+            else k_trace<true, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
             mark(T_SHADOW);
-            launches += 2; ++launches_shadow;
+            launches += PBRS_NUM_CLS + 1; ++launches_shadow;
         }
         if (tg.only_sample >= 0) {
             k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
@@ -436,9 +485,9 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         std::memset(st, 0, sizeof *st);
         uint64_t rays_extend = 0;
         for (uint32_t b = 0; b < n_batches; ++b)
-            for (int stage = 0; stage < n_stages; ++stage) rays_extend += counts[(size_t)b * PBRS_COUNTS_PER_BATCH + 2 * stage];
+            for (int stage = 0; stage < n_stages; ++stage) rays_extend += counts[(size_t)b * PBRS_COUNTS_PER_BATCH + PBRS_CNT_STRIDE * stage + PBRS_CNT_EXTEND];
         st->n_samples = counts.empty() ? 0 : 0;
-        for (uint32_t b = 0; b < n_batches; ++b) st->n_samples += counts[(size_t)b * PBRS_COUNTS_PER_BATCH];
+        for (uint32_t b = 0; b < n_batches; ++b) st->n_samples += counts[(size_t)b * PBRS_COUNTS_PER_BATCH + PBRS_CNT_EXTEND];
         st->n_rays_extend = rays_extend;
         st->n_rays_shadow = stats[kStatShadowRays];
         for (int k = 0; k < 4; ++k) { st->trav_extend[k] = stats[kStatTrav + k]; st->trav_shadow[k] = stats[kStatTrav + 4 + k]; }

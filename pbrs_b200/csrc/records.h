@@ -69,7 +69,8 @@ static_assert(sizeof(InstTravRec) == 64, "InstTravRec must be 64 bytes");
 struct InstShadeRec {
     float fwd[3][4];
     uint32_t material;
-    uint32_t pad[3];
+    uint32_t cls;  // PBRS_CLS_* of the material: which shade queue a hit on this instance joins
+    uint32_t pad[2];
 };
 static_assert(sizeof(InstShadeRec) == 64, "InstShadeRec must be 64 bytes");
 
@@ -85,6 +86,16 @@ struct MeshRec {
     uint32_t pad[4];
 };
 static_assert(sizeof(MeshRec) == 64, "MeshRec must be 64 bytes");
+
+// Material classes: one shade queue and one specialised shade kernel each (DESIGN.md "Wavefront").
+#define PBRS_CLS_ANY (-1)        // not specialised (host-sim / generic code)
+#define PBRS_CLS_MISS 0          // the ray left the scene
+#define PBRS_CLS_EMISSIVE 1      // DiffuseLight: no lobes
+#define PBRS_CLS_LAMBERT 2       // Lambertian, Substrate: one Lambert lobe
+#define PBRS_CLS_MICROFACET 3    // Metal, Glossy: one Torrance-Sparrow lobe
+#define PBRS_CLS_SPECULAR 4      // Mirror, Dielectric: one specular lobe
+#define PBRS_CLS_MULTI 5         // Plastic, Uber: several lobes
+#define PBRS_NUM_CLS 6
 
 #define PBRS_TEX_SOLID 0
 #define PBRS_TEX_IMAGE 1

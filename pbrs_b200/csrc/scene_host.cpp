@@ -500,6 +500,13 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
         trav[i].shape_index = s.shapes[in.shape].index;
         trav[i].identity = in.identity ? 1u : 0u;
         shade[i].material = (uint32_t)in.material;
+        switch (s.materials[in.material].kind) {
+        case PBRS_MTL_LAMBERTIAN: case PBRS_MTL_SUBSTRATE: shade[i].cls = PBRS_CLS_LAMBERT; break;
+        case PBRS_MTL_METAL: case PBRS_MTL_GLOSSY: shade[i].cls = PBRS_CLS_MICROFACET; break;
+        case PBRS_MTL_MIRROR: case PBRS_MTL_DIELECTRIC: shade[i].cls = PBRS_CLS_SPECULAR; break;
+        case PBRS_MTL_DIFFUSE_LIGHT: shade[i].cls = PBRS_CLS_EMISSIVE; break;
+        default: shade[i].cls = PBRS_CLS_MULTI; break;
+        }
     }
 
     // ---- textures ----

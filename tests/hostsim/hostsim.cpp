@@ -53,12 +53,13 @@ struct Sim {
     std::vector<f4> a[12];
     std::vector<u4> hit;
     std::vector<float> sh_m;
-    std::vector<uint32_t> q0, q1, sq;
+    std::vector<uint32_t> q0, q1, sq, cq[PBRS_NUM_CLS];
     PathBuffers pb{};
     void resize(uint32_t n) {
         for (auto &v : a) v.assign(n, f4{0, 0, 0, 0});
         hit.assign(n, u4{0, 0, 0, 0}); sh_m.assign(n, 0.0f);
         q0.assign(n, 0); q1.assign(n, 0); sq.assign(n, 0);
+        for (int c = 0; c < PBRS_NUM_CLS; ++c) { cq[c].assign(n, 0); pb.cls_queue[c] = cq[c].data(); }
         pb.ray_o = a[0].data(); pb.ray_d = a[1].data(); pb.hit = hit.data(); pb.beta = a[2].data(); pb.rad = a[3].data();
         pb.aux = a[4].data(); pb.sh_o1 = a[5].data(); pb.sh_d1 = a[6].data(); pb.sh_o2 = a[7].data(); pb.sh_d2 = a[8].data();
         pb.sh_c = a[9].data(); pb.sh_b = a[10].data(); pb.sh_m = sh_m.data();
@@ -81,6 +82,22 @@ struct Totals {
 void note(Totals &t, Diag &dg) {
     for (int k = 0; k < 16; ++k) if (dg.panics & (1u << k)) t.panic[k]++;
     dg.panics = 0;
+}
+
+template <int CLS>
+ShadeOut shade_cls(int integrator, const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j, int stage, Diag &dg) {
+    return integrator == PBRS_INTEGRATOR_PATH ? stage_shade_path<CLS>(sc, pb, fp, bp, j, stage, dg) : stage_shade_direct<CLS>(sc, pb, fp, bp, j, stage, dg);
+}
+ShadeOut shade_dispatch(int cls, int integrator, const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j,
+                        int stage, Diag &dg) {
+    switch (cls) {
+    case PBRS_CLS_MISS: return shade_cls<PBRS_CLS_MISS>(integrator, sc, pb, fp, bp, j, stage, dg);
+    case PBRS_CLS_EMISSIVE: return shade_cls<PBRS_CLS_EMISSIVE>(integrator, sc, pb, fp, bp, j, stage, dg);
+    case PBRS_CLS_LAMBERT: return shade_cls<PBRS_CLS_LAMBERT>(integrator, sc, pb, fp, bp, j, stage, dg);
+    case PBRS_CLS_MICROFACET: return shade_cls<PBRS_CLS_MICROFACET>(integrator, sc, pb, fp, bp, j, stage, dg);
+    case PBRS_CLS_SPECULAR: return shade_cls<PBRS_CLS_SPECULAR>(integrator, sc, pb, fp, bp, j, stage, dg);
+    default: return shade_cls<PBRS_CLS_MULTI>(integrator, sc, pb, fp, bp, j, stage, dg);
+    }
 }
 
 // mirrors render_frame (kernels.cu) for the tile range [tile_begin, tile_end) of the tile list
@@ -109,15 +126,25 @@ void run_tiles(const SceneImpl &s, FrameParams fp, const std::vector<uint32_t> &
             tot.te[0] += tc.nodes; tot.te[1] += tc.tris; tot.te[2] += tc.spheres; tot.te[3] += tc.insts;
             const TravCount te_snapshot = tc;
             if (fp.only_sample >= 0) { tot.nodes += tc.nodes; tot.tris += tc.tris; tot.spheres += tc.spheres; tot.insts += tc.insts; break; }
+            // like the extend kernel: every finished walk joins the shade queue of its material class,
+            // and each class runs its own specialisation of the shade stage
+            uint32_t n_cls[PBRS_NUM_CLS] = {0};
             for (uint32_t i = 0; i < n_in; ++i) {
                 uint32_t j = q_in[i];
-                ShadeOut so = fp.integrator == PBRS_INTEGRATOR_PATH ? stage_shade_path(sc, pb, fp, bp, j, stage, dg)
-                                                                    : stage_shade_direct(sc, pb, fp, bp, j, stage, dg);
-                note(tot, dg);
-                if (so.next) q_out[n_out++] = j;
-                if (so.shadow_rays > 0) pb.shadow_queue[n_sh++] = j;
-                tot.rays_shadow += (uint64_t)so.shadow_rays;
+                u4 hr = pb.hit[j];
+                Hit h; h.t = u2f(hr.x); h.inst = hr.y; h.tri = hr.z;
+                uint32_t c = hit_class(sc, h);
+                pb.cls_queue[c][n_cls[c]++] = j;
             }
+            for (int c = 0; c < PBRS_NUM_CLS; ++c)
+                for (uint32_t i = 0; i < n_cls[c]; ++i) {
+                    uint32_t j = pb.cls_queue[c][i];
+                    ShadeOut so = shade_dispatch(c, fp.integrator, sc, pb, fp, bp, j, stage, dg);
+                    note(tot, dg);
+                    if (so.next) q_out[n_out++] = j;
+                    if (so.shadow_rays > 0) pb.shadow_queue[n_sh++] = j;
+                    tot.rays_shadow += (uint64_t)so.shadow_rays;
+                }
             for (uint32_t i = 0; i < n_sh; ++i) { stage_shadow<true>(sc, pb, pb.shadow_queue[i], dg, tc); note(tot, dg); }
             tot.ts[0] += tc.nodes - te_snapshot.nodes; tot.ts[1] += tc.tris - te_snapshot.tris;
             tot.ts[2] += tc.spheres - te_snapshot.spheres; tot.ts[3] += tc.insts - te_snapshot.insts;

@@ -11,7 +11,8 @@ import subprocess
 from . import _capi as K
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpbrs_gpu.so")
+# PBRS_GPU_LIB: development knob to load an alternative build of the same library (kernel tuning)
+LIB_PATH = os.environ.get("PBRS_GPU_LIB") or os.path.join(_HERE, "lib", "libpbrs_gpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _api = None

@@ -5,9 +5,9 @@
 // lets a lane that is deep inside a mesh run alone while its 31 neighbours wait at the TLAS
 // level (ncu on the first version: 7-11 of 32 lanes active, profiles/r1_v0_*).  Here every
 // lane, whatever level it is on, meets the others in the same two phases of `step()`:
-//     phase 1  while the lane's next visit is an inner node: fetch its 64-byte record, test both
-//              child boxes, choose / push                       (the hot loop, shared by TLAS and BLAS)
-//     phase 2  one leaf (triangle run, sphere, or instance entry) or one stack unwind
+//     phase 1  until the lane stands at a leaf: expand inner nodes (fetch the 64-byte record, test
+//              both child boxes, choose / push) and unwind the stack   (the hot loop, TLAS and BLAS alike)
+//     phase 2  one leaf: a triangle run, a sphere, or an instance entry
 // and the kernels (kernels.cu) refill finished lanes from the ray queue between steps.
 //
 // Exactness (DESIGN.md "Traversal"): the visit order, the extent each box/primitive is tested
@@ -37,6 +37,18 @@ struct BoxTest {
     float tl;      // t_low, approximate (within the margin) or exact
 };
 
+// The reference's slab test with its true divisions; out of line, it is the rare path.
+PB_CALL BoxTest box_exact(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 o, vec3 d, float t_max) {
+    Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
+    float tl, me;
+    slab(mnx, mny, mnz, mxx, mxy, mxz, ray, tl, me);
+    BoxTest r;
+    r.pass = box_pass(tl, me, t_max);
+    r.overlap = !(tl > me);
+    r.tl = tl;
+    return r;
+}
+
 // One child box against the ray.  `fast` = the ray's direction has no zero / non-finite
 // reciprocal, so the products below are finite or overflow to inf (never NaN).
 PB_DEV BoxTest test_box(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 o, vec3 d, vec3 rd, bool fast, float t_max) {
@@ -58,13 +70,7 @@ PB_DEV BoxTest test_box(float mnx, float mny, float mnz, float mxx, float mxy, f
             return r;
         }
     }
-    Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
-    float tl, me;
-    slab(mnx, mny, mnz, mxx, mxy, mxz, ray, tl, me);
-    r.pass = box_pass(tl, me, t_max);
-    r.overlap = !(tl > me);
-    r.tl = tl;
-    return r;
+    return box_exact(mnx, mny, mnz, mxx, mxy, mxz, o, d, t_max);
 }
 // Re-test of a stacked child against the extent of the moment (it overlapped when pushed):
 // pass iff t_low <= t_max.  Returns 1 pass, 0 fail, -1 too close to call with an approximate tl.
@@ -120,15 +126,12 @@ struct Walk {
     PB_DEV const NodeRec *node_ptr(const DeviceScene &sc, uint32_t idx) const {
         return lvl ? sc.blas_nodes + mesh.node_base + idx : sc.tlas_nodes + idx;
     }
-    // exact t_low / pass of child `side` of node `par` (the rare re-test)
+    // exact pass of child `side` of node `par` (the rare re-test)
     PB_DEV bool exact_child(const DeviceScene &sc, uint32_t par, float extent) const {
         const char *b = reinterpret_cast<const char *>(node_ptr(sc, par & 0x7FFFFFFFu));
         f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32);
-        Ray ray; ray.o = o; ray.d = d; ray.t_max = extent;
-        float tl, me;
-        if (par & 0x80000000u) slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ray, tl, me);
-        else slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ray, tl, me);
-        return box_pass(tl, me, extent);
+        if (par & 0x80000000u) return box_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, extent).pass;
+        return box_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, extent).pass;
     }
 
     // ---- start: the root box with the ray's own extent (tlas/src/bvh.rs:78,106) ----
@@ -141,7 +144,13 @@ struct Walk {
         next = sc.tlas_root_is_leaf ? PBRS_LEAF_BIT : 0u;
     }
 
-    PB_DEV bool at_inner() const { return !done && next != PBRS_NONE && !(next & PBRS_LEAF_BIT); }
+    PB_DEV bool at_leaf() const { return !done && next != PBRS_NONE && (next & PBRS_LEAF_BIT); }
+    // phase 1: expansions and stack unwinds until the lane stands at a leaf (or is done)
+    PB_DEV bool advancing() const { return !done && !(next != PBRS_NONE && (next & PBRS_LEAF_BIT)); }
+    PB_DEV void advance(const DeviceScene &sc, Diag &dg, TravCount &tc) {
+        if (next != PBRS_NONE) expand(sc, dg, tc);
+        if (!done && next == PBRS_NONE) unwind(sc, dg);  // dead end: pop right away, same iteration
+    }
 
     // ---- phase 1: expand the inner node `next` ----
     PB_DEV void expand(const DeviceScene &sc, Diag &dg, TravCount &tc) {
@@ -302,18 +311,12 @@ struct Walk {
         }
     }
 
-    // one step of phase 2 (call when !at_inner() && !done)
-    PB_DEV void step2(const DeviceScene &sc, Diag &dg, TravCount &tc) {
-        if (next != PBRS_NONE) leaf(sc, dg, tc);
-        if (!done && next == PBRS_NONE) unwind(sc, dg);
-    }
-
     // the whole walk, sequentially (host-sim and single-ray callers)
     PB_DEV void run(const DeviceScene &sc, const Ray &ray, Diag &dg, TravCount &tc) {
         begin(sc, ray);
         while (!done) {
-            while (at_inner()) expand(sc, dg, tc);
-            if (!done) step2(sc, dg, tc);
+            while (advancing()) advance(sc, dg, tc);
+            if (at_leaf()) leaf(sc, dg, tc);
         }
     }
 };

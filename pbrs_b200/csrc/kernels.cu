@@ -74,7 +74,14 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 // Every lane owns one Walk; the warp alternates phase 1 (inner-node expansions, all levels) and
 // phase 2 (one leaf or unwind) and, whenever enough lanes have run dry, draws the next rays from
 // the queue with a single atomicAdd on the launch's work cursor.
-constexpr int kRefillIdleLanes = 10;  // refill as soon as this many lanes are idle
+#ifndef PBRS_REFILL_IDLE_LANES
+#define PBRS_REFILL_IDLE_LANES 24
+#endif
+constexpr int kRefillIdleLanes = PBRS_REFILL_IDLE_LANES;  // refill as soon as this many lanes are idle
+#ifndef PBRS_LEAF_VOTE
+#define PBRS_LEAF_VOTE 8
+#endif
+constexpr int kLeafVote = PBRS_LEAF_VOTE;  // leave phase 1 once this many lanes wait at a leaf (32: all of them)
 
 // `cnt` = this stage's counter block (PBRS_CNT_*).
 template <bool ANY, bool COUNT>
@@ -119,11 +126,21 @@ __global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers 
         } else if (idle == 0xFFFFFFFFu) {
             break;
         }
-        // ---- phase 1: inner nodes ----
-        while (busy && w.at_inner()) w.expand(sc, dg, tc);
+        // ---- phase 1: expansions / unwinds until every busy lane stands at a leaf or is done ----
+        if (kLeafVote >= 32) {
+            while (busy && w.advancing()) w.advance(sc, dg, tc);
+        } else {
+            while (true) {
+                const bool adv = busy && w.advancing();
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, adv);
+                const unsigned waiting = __ballot_sync(0xFFFFFFFFu, busy && w.at_leaf());
+                if (m == 0u || __popc(waiting) >= kLeafVote) break;
+                if (adv) w.advance(sc, dg, tc);
+            }
+        }
         __syncwarp();
-        // ---- phase 2: one leaf / unwind ----
-        if (busy && !w.done) w.step2(sc, dg, tc);
+        // ---- phase 2: one leaf ----
+        if (busy && w.at_leaf()) w.leaf(sc, dg, tc);
         if (ANY) {
             if (busy && w.done) {
                 if (!w.occluded) vis |= 1u << which;

@@ -84,8 +84,11 @@ constexpr int kRefillIdleLanes = PBRS_REFILL_IDLE_LANES;  // refill as soon as t
 constexpr int kLeafVote = PBRS_LEAF_VOTE;  // leave phase 1 once this many lanes wait at a leaf (32: all of them)
 
 // `cnt` = this stage's counter block (PBRS_CNT_*).
+#ifndef PBRS_TRACE_BLOCKS_PER_SM
+#define PBRS_TRACE_BLOCKS_PER_SM 8
+#endif
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
+__global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
     const uint32_t *count = cnt + (ANY ? PBRS_CNT_SHADOW : PBRS_CNT_EXTEND);
     uint32_t *cursor = cnt + (ANY ? PBRS_CNT_SHADOW_CURSOR : PBRS_CNT_EXTEND_CURSOR);
     Diag dg; dg.panics = 0u;

@@ -219,15 +219,20 @@ PB_DEV bool sphere_occludes(vec3 c, float radius, const Ray &r) {
 }
 // The full Interaction of Sphere::intersect in the sphere's own space.  D1: a hit from
 // inside trips Interaction::new's assert upstream; flag it and face the normal to the ray.
-PB_DEV bool sphere_intersect(vec3 c, float radius, const Ray &r, Isect &out, Diag &dg) {
+// need_uv = false skips the (u, v) of the hit (two FP64 transcendentals): only image textures read them.
+PB_DEV bool sphere_intersect(vec3 c, float radius, const Ray &r, Isect &out, Diag &dg, bool need_uv = true) {
     float ray_t;
     if (!sphere_hit_t(c, radius, r, ray_t)) return false;
     vec3 pos = at(r, ray_t);
     vec3 normal = hat(pos - c, dg);
     pos = c + normal * radius * 1.00001f;
-    float theta = t_acos(normal.y);
-    float phi = t_atan2(normal.z, normal.x) + kPi;
-    float u = phi / (2.0f * kPi), v = theta / kPi;
+    float u = 0.0f, v = 0.0f;
+    if (need_uv) {
+        float theta = t_acos(normal.y);
+        float phi = t_atan2(normal.z, normal.x) + kPi;
+        u = phi / (2.0f * kPi);
+        v = theta / kPi;
+    }
     vec3 dpdu;
     if (!try_hat(mk(-normal.y, normal.x, 0.0f), dpdu)) dpdu = mk(1.0f, 0.0f, 0.0f);
     if (!(len(pos - c) >= radius)) flag(dg, P_MISC);

@@ -638,7 +638,7 @@ PB_DEV AreaLight load_area_light(const AreaLightRec *r) {
 PB_CALL bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, vec3 &normal, Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) {
         Isect h;
-        if (!sphere_intersect(l.p0, l.p1.x, r, h, dg)) return false;
+        if (!sphere_intersect(l.p0, l.p1.x, r, h, dg, false)) return false;
         pos = h.pos; normal = h.normal;
         return true;
     }

@@ -193,10 +193,12 @@ PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32
     wr.t_max = PB_INF;
     uint32_t kind, index;
     Ray o = to_object(sc.inst_trav + inst, wr, kind, index);
+    const char *sb = reinterpret_cast<const char *>(sc.inst_shade + inst);
+    const f4 tail = ld16(sb + 48);
     Isect h;
     if (kind == PBRS_SHAPE_SPHERE) {
         f4 s = ld16(sc.spheres + index);
-        sphere_intersect(mk(s.x, s.y, s.z), s.w, o, h, dg);
+        sphere_intersect(mk(s.x, s.y, s.z), s.w, o, h, dg, f2u(tail.z) != 0u);
     } else {
         MeshHead m = load_mesh_head(sc.meshes + index);
         TriVerts tv = load_tri(sc.tris + tri);
@@ -207,9 +209,8 @@ PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32
         with_dpdu(h, mh.dpdu, dg);
     }
     const char *tb = reinterpret_cast<const char *>(sc.inst_trav + inst);
-    const char *sb = reinterpret_cast<const char *>(sc.inst_shade + inst);
     f4 i0 = ld16(tb), i1 = ld16(tb + 16), i2 = ld16(tb + 32);
-    f4 f0 = ld16(sb), f1 = ld16(sb + 16), f2 = ld16(sb + 32), tail = ld16(sb + 48);
+    f4 f0 = ld16(sb), f1 = ld16(sb + 16), f2 = ld16(sb + 32);
     material = f2u(tail.x);
     vec3 new_pos = mk(row_pt(f0, h.pos), row_pt(f1, h.pos), row_pt(f2, h.pos));
     vec3 new_wo = mk(row_vec(f0, h.wo), row_vec(f1, h.wo), row_vec(f2, h.wo));

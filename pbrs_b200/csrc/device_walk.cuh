@@ -72,6 +72,40 @@ PB_DEV BoxTest test_box(float mnx, float mny, float mnz, float mxx, float mxy, f
     }
     return box_exact(mnx, mny, mnz, mxx, mxy, mxz, o, d, t_max);
 }
+// Both child boxes of a node at once: one pre-test, one shared branch to the exact path.
+// need_overlap: the caller also wants `overlap` of the right child (TLAS closest-hit only).
+struct PairTest {
+    BoxTest l, r;
+};
+PB_DEV PairTest test_pair(f4 q0, f4 q1, f4 q2, vec3 o, vec3 d, vec3 rd, bool fast, float t_max, bool need_overlap) {
+    PairTest p;
+    if (fast) {
+        float ax = (q0.x - o.x) * rd.x, bx = (q0.w - o.x) * rd.x, cx = (q1.z - o.x) * rd.x, dx = (q2.y - o.x) * rd.x;
+        float ay = (q0.y - o.y) * rd.y, by = (q1.x - o.y) * rd.y, cy = (q1.w - o.y) * rd.y, dy = (q2.z - o.y) * rd.y;
+        float az = (q0.z - o.z) * rd.z, bz = (q1.y - o.z) * rd.z, cz = (q2.x - o.z) * rd.z, dz = (q2.w - o.z) * rd.z;
+        float ltl = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), 0.0f);
+        float lme = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        float rtl = fmaxf(fmaxf(fmaxf(fminf(cx, dx), fminf(cy, dy)), fminf(cz, dz)), 0.0f);
+        float rme = fminf(fminf(fmaxf(cx, dx), fmaxf(cy, dy)), fmaxf(cz, dz));
+        // margins (explicit fma: this is the approximate side, contraction is harmless here)
+        float lm = fmaf(PBRS_BOX_MARGIN, ltl, PBRS_BOX_TINY), ln = fmaf(PBRS_BOX_MARGIN, fabsf(lme), PBRS_BOX_TINY);
+        float rm = fmaf(PBRS_BOX_MARGIN, rtl, PBRS_BOX_TINY), rn = fmaf(PBRS_BOX_MARGIN, fabsf(rme), PBRS_BOX_TINY);
+        // pass = tl <= min(me, t_max): surely yes / surely no
+        bool l_yes = ltl + lm <= fminf(lme - ln, t_max), l_no = ltl - lm > fminf(lme + ln, t_max);
+        bool r_yes = rtl + rm <= fminf(rme - rn, t_max), r_no = rtl - rm > fminf(rme + rn, t_max);
+        bool sure = (l_yes || l_no) && (r_yes || r_no);  // false whenever a value is inf / NaN
+        bool r_ov_yes = rtl + rm <= rme - rn;
+        if (need_overlap) sure = sure && (r_ov_yes || rtl - rm > rme + rn);
+        if (sure) {
+            p.l.pass = l_yes; p.l.overlap = l_yes; p.l.tl = ltl;
+            p.r.pass = r_yes; p.r.overlap = r_ov_yes; p.r.tl = rtl;
+            return p;
+        }
+    }
+    p.l = box_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, t_max);
+    p.r = box_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, t_max);
+    return p;
+}
 // Re-test of a stacked child against the extent of the moment (it overlapped when pushed):
 // pass iff t_low <= t_max.  Returns 1 pass, 0 fail, -1 too close to call with an approximate tl.
 PB_DEV int retest(float tl, float t_max) {
@@ -158,13 +192,15 @@ struct Walk {
         const uint32_t self = next;
         const char *b = reinterpret_cast<const char *>(node_ptr(sc, self));
         f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32), q3 = ld16(b + 48);
-        BoxTest L = test_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, rd, fast, t_max);
-        BoxTest R = test_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, rd, fast, t_max);
+        const PairTest pt = test_pair(q0, q1, q2, o, d, rd, fast, t_max, !ANY && lvl == 0u);
+        const BoxTest &L = pt.l, &R = pt.r;
         uint32_t meta = f2u(q3.z);
         uint32_t lref = f2u(q3.x) | ((meta & PBRS_NODE_LEFT_LEAF) ? PBRS_LEAF_BIT : 0u);
         uint32_t rref = f2u(q3.y) | ((meta & PBRS_NODE_RIGHT_LEAF) ? PBRS_LEAF_BIT : 0u);
         if (ANY) {
-            // `left || right`, depth first; the extent never changes, so a pass is final
+            // `left || right`, depth first (tlas/src/bvh.rs:105-113, blas.rs:478-495); the extent
+            // never changes, so a pass is final.  (Visiting the nearer child first was measured:
+            // 4 % MORE nodes on the C4 scene, so the reference's order stays.)
             if (L.pass) {
                 if (R.pass) push(rref, 0.0f, 0u, dg);
                 next = lref;

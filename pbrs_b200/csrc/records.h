@@ -70,7 +70,8 @@ struct InstShadeRec {
     float fwd[3][4];
     uint32_t material;
     uint32_t cls;  // PBRS_CLS_* of the material: which shade queue a hit on this instance joins
-    uint32_t pad[2];
+    uint32_t uses_uv;  // the material reads an image texture, i.e. the hit's (u, v) are consumed
+    uint32_t pad;
 };
 static_assert(sizeof(InstShadeRec) == 64, "InstShadeRec must be 64 bytes");
 

@@ -500,6 +500,13 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
         trav[i].shape_index = s.shapes[in.shape].index;
         trav[i].identity = in.identity ? 1u : 0u;
         shade[i].material = (uint32_t)in.material;
+        {
+            const MaterialRec &mr = s.materials[in.material];
+            const int ids[4] = {mr.tex_kd, mr.tex_ks, mr.tex_kr, mr.tex_kt};
+            shade[i].uses_uv = 0u;
+            for (int id : ids)
+                if (id >= 0 && id < (int)s.textures.size() && s.textures[id].rec.kind == PBRS_TEX_IMAGE) shade[i].uses_uv = 1u;
+        }
         switch (s.materials[in.material].kind) {
         case PBRS_MTL_LAMBERTIAN: case PBRS_MTL_SUBSTRATE: shade[i].cls = PBRS_CLS_LAMBERT; break;
         case PBRS_MTL_METAL: case PBRS_MTL_GLOSSY: shade[i].cls = PBRS_CLS_MICROFACET; break;

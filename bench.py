@@ -144,7 +144,7 @@ def run_reference(args):
     cores = api["get_threads"]()
     H, W = h.height, h.width
     # size the per-step sample for ~8 s
-    st, dt, n_rows, step = cpu_sample(h, integrator, msaa, target_s=8.0)
+    st, dt, n_rows, step = cpu_sample(h, integrator, msaa)  # the same bounded sample as the cpu_baseline leg of the GPU arm
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
@@ -298,7 +298,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wname, "integrator": integrator, "spp": spp, "max_depth": 5, "resolution": [W, H],
                        "split": split if world > 1 else "none", "l2": "path state streamed per batch exceeds L2 (inputs larger than L2)",
-                       "paths_in_flight": args.paths_in_flight or (1 << 22)},
+                       "paths_in_flight": args.paths_in_flight or (1 << 24)},
             "mrays_per_s": (n_ext + n_sh) / (ms_step * 1e-3) / 1e6,
             "frame_ms": ms_step,
             "clocks": clk,

@@ -121,9 +121,10 @@ struct Walk {
     vec3 o, d, rd;
     float t_max;
     bool fast;
-    // the world ray while inside an instance
-    vec3 wo, wd;
+    // the world ray (and its reciprocal direction) while inside an instance
+    vec3 wo, wd, wrd;
     float w_t_max;
+    bool wfast;
     uint32_t next;  // ref to visit (PBRS_LEAF_BIT = leaf), PBRS_NONE = unwind
     uint32_t lvl;   // 0 = TLAS, 1 = inside a mesh instance
     int sp;
@@ -148,6 +149,7 @@ struct Walk {
         rd = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         fast = is_fin(rd.x) && is_fin(rd.y) && is_fin(rd.z) && !any_nan(o);
     }
+    PB_DEV void restore_world() { o = wo; d = wd; rd = wrd; t_max = w_t_max; fast = wfast; }
     PB_DEV void push(uint32_t ref, float tl, uint32_t par, Diag &dg) {
         if (sp < PBRS_WALK_STACK) {
             st_ref[sp] = ref;
@@ -281,11 +283,11 @@ struct Walk {
         }
         // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
         mesh = load_mesh_head(sc.meshes + index);
-        wo = o; wd = d; w_t_max = t_max;
+        wo = o; wd = d; wrd = rd; w_t_max = t_max; wfast = fast;
         set_space(obj.o, obj.d, obj.t_max);
         BoxTest rb = test_box(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], o, d, rd, fast, t_max);
         if (!rb.pass) {
-            set_space(wo, wd, w_t_max);
+            restore_world();
             if (!ANY) ret = PB_INF;
             return;
         }
@@ -311,7 +313,7 @@ struct Walk {
                 if (ref == PBRS_TAG_EXIT) {
                     // the mesh walk is over: back to the world ray
                     lvl = 0u;
-                    set_space(wo, wd, w_t_max);
+                    restore_world();
                     if (ANY) continue;
                     if (l_best_t < PB_INF) {
                         ret = l_best_t;

@@ -416,7 +416,8 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     if (tg.only_sample >= 0) n_stages = 1;
     if (n_stages > PBRS_MAX_STAGES) { set_error("max_depth too large (at most 15 bounces)"); return PBRS_ERR_INVALID_ARG; }
 
-    uint32_t capacity = o.paths_in_flight ? o.paths_in_flight : (1u << 22);
+    // default 16 Mi paths (~4 GB of path state): measured +15 % over 4 Mi (fewer, longer launches; tails amortised)
+    uint32_t capacity = o.paths_in_flight ? o.paths_in_flight : (1u << 24);
     const uint64_t total_pixels = (uint64_t)fp.n_tiles * 4096u;
     const uint64_t total_paths = total_pixels * fp.spp_r;
     if (total_paths < capacity) capacity = (uint32_t)std::max<uint64_t>(total_paths, 32);

@@ -121,10 +121,8 @@ struct Walk {
     vec3 o, d, rd;
     float t_max;
     bool fast;
-    // the world ray (and its reciprocal direction) while inside an instance
-    vec3 wo, wd, wrd;
-    float w_t_max;
-    bool wfast;
+    // (while a lane is inside a mesh instance its world ray, reciprocal direction and extent wait
+    // on the stack under the walk's entries -- see enter_mesh / leave_mesh -- not in registers)
     uint32_t next;  // ref to visit (PBRS_LEAF_BIT = leaf), PBRS_NONE = unwind
     uint32_t lvl;   // 0 = TLAS, 1 = inside a mesh instance
     int sp;
@@ -135,7 +133,7 @@ struct Walk {
     // the mesh instance being walked
     float l_best_t;
     uint32_t l_best_tri, cur_inst;
-    MeshHead mesh;
+    uint32_t node_base, tri_base, mesh_index;  // of that mesh
     float ret;  // TLAS closest: value of the subtree that just completed
     // the stack lives in arrays owned by the caller (so that the scalars above stay in registers)
     uint32_t *st_ref;
@@ -149,7 +147,28 @@ struct Walk {
         rd = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         fast = is_fin(rd.x) && is_fin(rd.y) && is_fin(rd.z) && !any_nan(o);
     }
-    PB_DEV void restore_world() { o = wo; d = wd; rd = wrd; t_max = w_t_max; fast = wfast; }
+    // Eleven words of world-ray state parked on the stack for the duration of a mesh walk.
+    PB_DEV void park(uint32_t a, uint32_t b, uint32_t c, Diag &dg) {
+        if (ANY) { push(a, 0.0f, 0u, dg); push(b, 0.0f, 0u, dg); push(c, 0.0f, 0u, dg); }
+        else push(a, u2f(b), c, dg);
+    }
+    PB_DEV void unpark(uint32_t &a, uint32_t &b, uint32_t &c) {
+        if (ANY) { c = st_ref[sp - 1]; b = st_ref[sp - 2]; a = st_ref[sp - 3]; sp -= 3; }
+        else { --sp; a = st_ref[sp]; b = f2u(st_tl[sp]); c = st_par[sp]; }
+    }
+    PB_DEV void save_world(Diag &dg) {
+        park(f2u(o.x), f2u(o.y), f2u(o.z), dg);
+        park(f2u(d.x), f2u(d.y), f2u(d.z), dg);
+        park(f2u(rd.x), f2u(rd.y), f2u(rd.z), dg);
+        park(f2u(t_max), fast ? 1u : 0u, 0u, dg);
+    }
+    PB_DEV void restore_world() {
+        uint32_t a, b, c;
+        unpark(a, b, c); t_max = u2f(a); fast = b != 0u;
+        unpark(a, b, c); rd = mk(u2f(a), u2f(b), u2f(c));
+        unpark(a, b, c); d = mk(u2f(a), u2f(b), u2f(c));
+        unpark(a, b, c); o = mk(u2f(a), u2f(b), u2f(c));
+    }
     PB_DEV void push(uint32_t ref, float tl, uint32_t par, Diag &dg) {
         if (sp < PBRS_WALK_STACK) {
             st_ref[sp] = ref;
@@ -160,7 +179,7 @@ struct Walk {
         }
     }
     PB_DEV const NodeRec *node_ptr(const DeviceScene &sc, uint32_t idx) const {
-        return lvl ? sc.blas_nodes + mesh.node_base + idx : sc.tlas_nodes + idx;
+        return lvl ? sc.blas_nodes + node_base + idx : sc.tlas_nodes + idx;
     }
     // exact pass of child `side` of node `par` (the rare re-test)
     PB_DEV bool exact_child(const DeviceScene &sc, uint32_t par, float extent) const {
@@ -233,7 +252,7 @@ struct Walk {
         if (lvl) {
             // a run of triangles (shape/src/blas.rs:447-454): all see the extent of the pop
             Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
-            uint32_t s = mesh.tri_base + first;
+            uint32_t s = tri_base + first;
             while (true) {
                 TriVerts tv = load_tri(sc.tris + s);
                 if (COUNT) tc.tris++;
@@ -244,7 +263,7 @@ struct Walk {
                     bool hit;
                     if (tv.flags & PBRS_TRI_CHECK_SHADING) {
                         MeshHit mh;
-                        hit = mesh_tri_shade(sc, mesh, tv, ray, mh, dg);
+                        hit = mesh_tri_shade(sc, load_mesh_head(sc.meshes + mesh_index), tv, ray, mh, dg);
                         t = mh.t;
                     } else {
                         TriHit h;
@@ -282,8 +301,8 @@ struct Walk {
             return;
         }
         // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
-        mesh = load_mesh_head(sc.meshes + index);
-        wo = o; wd = d; wrd = rd; w_t_max = t_max; wfast = fast;
+        const MeshHead mesh = load_mesh_head(sc.meshes + index);
+        save_world(dg);
         set_space(obj.o, obj.d, obj.t_max);
         BoxTest rb = test_box(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], o, d, rd, fast, t_max);
         if (!rb.pass) {
@@ -291,6 +310,7 @@ struct Walk {
             if (!ANY) ret = PB_INF;
             return;
         }
+        node_base = mesh.node_base; tri_base = mesh.tri_base; mesh_index = index;
         cur_inst = first;
         l_best_t = PB_INF; l_best_tri = PBRS_NONE;
         lvl = 1u;

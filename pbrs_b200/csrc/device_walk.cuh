@@ -160,11 +160,13 @@ struct Walk {
         park(f2u(o.x), f2u(o.y), f2u(o.z), dg);
         park(f2u(d.x), f2u(d.y), f2u(d.z), dg);
         park(f2u(rd.x), f2u(rd.y), f2u(rd.z), dg);
-        park(f2u(t_max), fast ? 1u : 0u, 0u, dg);
+        park(f2u(t_max), fast ? 1u : 0u, cur_inst, dg);
+        if (!ANY) park(f2u(best.t), best.inst, best.tri, dg);
     }
     PB_DEV void restore_world() {
         uint32_t a, b, c;
-        unpark(a, b, c); t_max = u2f(a); fast = b != 0u;
+        if (!ANY) { unpark(a, b, c); best.t = u2f(a); best.inst = b; best.tri = c; }
+        unpark(a, b, c); t_max = u2f(a); fast = b != 0u; cur_inst = c;
         unpark(a, b, c); rd = mk(u2f(a), u2f(b), u2f(c));
         unpark(a, b, c); d = mk(u2f(a), u2f(b), u2f(c));
         unpark(a, b, c); o = mk(u2f(a), u2f(b), u2f(c));
@@ -302,6 +304,7 @@ struct Walk {
         }
         // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
         const MeshHead mesh = load_mesh_head(sc.meshes + index);
+        cur_inst = first;
         save_world(dg);
         set_space(obj.o, obj.d, obj.t_max);
         BoxTest rb = test_box(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], o, d, rd, fast, t_max);
@@ -311,7 +314,6 @@ struct Walk {
             return;
         }
         node_base = mesh.node_base; tri_base = mesh.tri_base; mesh_index = index;
-        cur_inst = first;
         l_best_t = PB_INF; l_best_tri = PBRS_NONE;
         lvl = 1u;
         push(PBRS_TAG_EXIT, 0.0f, 0u, dg);

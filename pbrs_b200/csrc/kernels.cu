@@ -182,8 +182,11 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
 // One shade kernel per material class CLS (its queue was filled by the extend kernel) and
 // integrator: only the code of that class's lobes is compiled in, and the lanes of a warp run
 // the same material code.  `cnt` / `next_cnt` = counter blocks of this stage / the next one.
+#ifndef PBRS_SHADE_BLOCKS_PER_SM
+#define PBRS_SHADE_BLOCKS_PER_SM 4
+#endif
 template <int CLS, int INTEGRATOR>
-__global__ void __launch_bounds__(kThreads, 4) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
+__global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
                                                     uint32_t *next_queue, uint32_t *next_cnt, int bounce) {
     Diag dg; dg.panics = 0u;
     uint32_t rays = 0u;

@@ -106,6 +106,50 @@ def cornell_box(width=512, height=512):
     return sd
 
 
+def cornell_box_pbrt(width=512, height=512):
+    """The same Cornell box as pbrt-v3-subset TEXT, the form BASELINE configs[0] names ("via
+    scene_parser"): LookAt / Camera / Film, matte materials, `trianglemesh` walls and boxes under
+    Translate / Rotate, and an `AreaLightSource "diffuse"` on a `sphere` (the loader's area lights
+    accept only sphere / plymesh, scene/src/loader.rs:396-434)."""
+    def mesh(P, idx):
+        pts = " ".join(f"{v:g}" for v in np.asarray(P, np.float64).reshape(-1))
+        ind = " ".join(str(int(v)) for v in np.asarray(idx).reshape(-1))
+        return f'Shape "trianglemesh" "point P" [ {pts} ] "integer indices" [ {ind} ]'
+    S = 555.0
+    quads = [
+        (_quad((S, 0, 0), (S, S, 0), (S, S, S), (S, 0, S)), "green"),
+        (_quad((0, 0, 0), (0, S, 0), (0, S, S), (0, 0, S)), "red"),
+        (_quad((0, 0, 0), (S, 0, 0), (S, 0, S), (0, 0, S)), "white"),
+        (_quad((0, S, 0), (S, S, 0), (S, S, S), (0, S, S)), "white"),
+        (_quad((0, 0, S), (S, 0, S), (S, S, S), (0, S, S)), "white"),
+    ]
+    out = [
+        "# Cornell box, pbrt-v3 subset understood by pbrs (scene_parser + scene/src/loader.rs)",
+        "LookAt 278 278 -800  278 278 0  0 1 0",
+        'Camera "perspective" "float fov" [ 40 ]',
+        f'Film "image" "integer xresolution" [ {width} ] "integer yresolution" [ {height} ]',
+        "WorldBegin",
+        'MakeNamedMaterial "red" "string type" "matte" "rgb Kd" [ 0.65 0.05 0.05 ]',
+        'MakeNamedMaterial "white" "string type" "matte" "rgb Kd" [ 0.73 0.73 0.73 ]',
+        'MakeNamedMaterial "green" "string type" "matte" "rgb Kd" [ 0.12 0.45 0.15 ]',
+    ]
+    for (P, idx), m in quads:
+        out += ["AttributeBegin", f'  NamedMaterial "{m}"', "  " + mesh(P, idx), "AttributeEnd"]
+    for (lo, hi, t, deg) in [((0, 0, 0), (165, 165, 165), (265, 0, 105), 15.0), ((0, 0, 0), (165, 330, 165), (130, 0, 225), -18.0)]:
+        P, idx = _box(lo, hi)
+        # pbrs negates Rotate angles (loader.rs:792-798), so the file carries the opposite sign
+        out += ["AttributeBegin", '  NamedMaterial "white"', f"  Translate {t[0]} {t[1]} {t[2]}", f"  Rotate {-deg:g} 0 1 0", "  " + mesh(P, idx),
+                "AttributeEnd"]
+    out += ["AttributeBegin", '  AreaLightSource "diffuse" "rgb L" [ 15 15 15 ]', "  Translate 278 514 279.5", '  Shape "sphere" "float radius" [ 40 ]',
+            "AttributeEnd", "WorldEnd", ""]
+    return "\n".join(out)
+
+
+def cornell_box_via_parser(width=512, height=512):
+    from .pbrt_loader import load_pbrt_string
+    return load_pbrt_string(cornell_box_pbrt(width, height))
+
+
 def spheres500(width=1920, height=1080, n_small=496, seed=SEED):
     """C3: ground + 3 big + n_small small spheres, Lambertian/Metal/Dielectric, blue-sky env.
 
@@ -325,15 +369,15 @@ def _wh(w, h, s):
 
 # `s` scales the frame (1.0 = the BASELINE.json size); used only to shorten profiling runs
 CONFIGS = {
-    "c1": (lambda s=1.0: cornell_box(*_wh(512, 512, s)), "path", 4),
-    "c2": (lambda s=1.0: cornell_box(*_wh(1920, 1080, s)), "direct", 1),
+    "c1": (lambda s=1.0: cornell_box_via_parser(*_wh(512, 512, s)), "path", 4),
+    "c2": (lambda s=1.0: cornell_box_via_parser(*_wh(1920, 1080, s)), "direct", 1),
     "c3": (lambda s=1.0: spheres500(*_wh(1920, 1080, s)), "path", 8),
     "c4": (lambda s=1.0: mesh_terrain(*_wh(3840, 2160, s)), "path", 16),
     "c5": (lambda s=1.0: instanced_field(*_wh(3840, 2160, s)), "path", 32),
 }
 WORKLOAD_NAMES = {
-    "c1": "C1 cornell-box 512x512 16spp path depth5",
-    "c2": "C2 cornell-box 1920x1080 1spp direct",
+    "c1": "C1 cornell-box (pbrt text via the scene-file loader) 512x512 16spp path depth5",
+    "c2": "C2 cornell-box (pbrt text via the scene-file loader) 1920x1080 1spp direct",
     "c3": "C3 500-spheres 1920x1080 64spp path depth5",
     "c4": "C4 1M-triangle terrain 3840x2160 256spp path depth5",
     "c5": "C5 10k-instance field (~12.8M tris) 3840x2160 1024spp path depth5",

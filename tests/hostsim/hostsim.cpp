@@ -122,7 +122,11 @@ void run_tiles(const SceneImpl &s, FrameParams fp, const std::vector<uint32_t> &
             Diag dg; dg.panics = 0;
             TravCount tc{0, 0, 0, 0};
             tot.rays_extend += n_in;
-            for (uint32_t i = 0; i < n_in; ++i) { stage_extend<true>(sc, pb, q_in[i], dg, tc); note(tot, dg); }
+            const bool counting = (fp.flags & PBRS_FLAG_COUNT_TRAVERSAL) != 0;  // like the kernels: two instantiations
+            for (uint32_t i = 0; i < n_in; ++i) {
+                if (counting) stage_extend<true>(sc, pb, q_in[i], dg, tc); else stage_extend<false>(sc, pb, q_in[i], dg, tc);
+                note(tot, dg);
+            }
             tot.te[0] += tc.nodes; tot.te[1] += tc.tris; tot.te[2] += tc.spheres; tot.te[3] += tc.insts;
             const TravCount te_snapshot = tc;
             if (fp.only_sample >= 0) { tot.nodes += tc.nodes; tot.tris += tc.tris; tot.spheres += tc.spheres; tot.insts += tc.insts; break; }
@@ -145,7 +149,10 @@ void run_tiles(const SceneImpl &s, FrameParams fp, const std::vector<uint32_t> &
                     if (so.shadow_rays > 0) pb.shadow_queue[n_sh++] = j;
                     tot.rays_shadow += (uint64_t)so.shadow_rays;
                 }
-            for (uint32_t i = 0; i < n_sh; ++i) { stage_shadow<true>(sc, pb, pb.shadow_queue[i], dg, tc); note(tot, dg); }
+            for (uint32_t i = 0; i < n_sh; ++i) {
+                if (counting) stage_shadow<true>(sc, pb, pb.shadow_queue[i], dg, tc); else stage_shadow<false>(sc, pb, pb.shadow_queue[i], dg, tc);
+                note(tot, dg);
+            }
             tot.ts[0] += tc.nodes - te_snapshot.nodes; tot.ts[1] += tc.tris - te_snapshot.tris;
             tot.ts[2] += tc.spheres - te_snapshot.spheres; tot.ts[3] += tc.insts - te_snapshot.insts;
             tot.nodes += tc.nodes; tot.tris += tc.tris; tot.spheres += tc.spheres; tot.insts += tc.insts;

@@ -53,6 +53,16 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def measured_traffic(workload):
+    """DRAM bytes per k_trace<closest> launch from the committed ncu --set full capture of this
+    workload (profiles/r1_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get("extend_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def extend_bytes(st):
     """32 (ray read) + 64/inner node + 48/triangle + 16/sphere + 128/instance + 32 (hit write)."""
     n, t, s, i = st["trav_extend"]
@@ -306,10 +316,11 @@ def main():
                     "h2d_bytes_per_step": int(4 * ((W + 63) // 64) * ((H + 63) // 64)), "d2h_bytes_per_step": int(W * H * 12)},
             "gpu_launches": int(st_time["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS/BLAS walk)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": measured_traffic(args.workload) if args.frame_scale == 1.0 else None,
                          "algorithmic_bytes_per_launch": ext_b / n_launch, "ms_per_launch": ext_ms / n_launch, "launches_per_step": int(n_launch),
                          "bytes_per_ray": ext_b / max(1.0, st_count["n_rays_extend"]),
-                         "note": "scene records are L2-resident for this workload; see DESIGN.md"},
+                         "note": "achieved = algorithmic bytes (SURVEY 8d formula) / summed launch time; traffic = DRAM bytes per launch from ncu "
+                                 "(the BVH is largely L2-resident, so traffic << algorithmic bytes: the kernel is issue-bound, DESIGN.md section 6)"},
             "stages_ms": {k: st_time[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
             "shadow_kernel": {"achieved": shadow_bytes(st_count) / (sh_ms * 1e-3) / 1e9 if sh_ms > 0 else 0.0, "unit": "GB/s"},
             "would_panic": st_count["would_panic"],

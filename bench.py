@@ -194,6 +194,13 @@ def main():
         run_reference(args)
         return
 
+    # stdout must carry exactly ONE JSON line.  Native libraries (NCCL prints its version banner
+    # on fd 1) write there too, so fd 1 is pointed at stderr for the whole run and the JSON line
+    # goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -334,7 +341,8 @@ def main():
             line["cpu_baseline"] = {"value": stc["n_samples"] / dt / 1e6, "unit": "Msamples/s", "cores": oracle_ffi.load()["get_threads"](), "kind": "port",
                                     "sample": f"rows 0,{step},.. ({n_rows} of {H}) of the same frame at full spp, {dt:.1f} s",
                                     "mrays_per_s": (stc["n_rays_extend"] + stc["n_rays_shadow"]) / dt / 1e6}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

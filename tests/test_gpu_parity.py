@@ -50,6 +50,21 @@ def test_primary_hits_no_jitter_crop_and_edges(oracle_api, gpu_api):
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bits_equal(a[2], b[2]).all(), crop
 
 
+@pytest.mark.parametrize("name", ["edge_mesh", "edge_single", "cornell"])
+def test_axis_aligned_rays_no_jitter(oracle_api, gpu_api, name):
+    """PBRS_FLAG_NO_JITTER: the centre column / row rays have exactly-zero direction components
+    (infinite reciprocals, 0/0 slabs): the walker's exact-division path on the device."""
+    sd = SMALL_SCENES[name]()
+    ho, hg = sd.realize(oracle_api), sd.realize(gpu_api)
+    a = ho.render_ids(0, msaa=1, flags=4)
+    b = hg.render_ids(0, msaa=1, flags=4)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bits_equal(a[2], b[2]).all()
+    fa, sa = ho.render_samples(integrator="path", msaa=1, max_depth=4, flags=4 | 1)
+    fb, sb = hg.render_samples(integrator="path", msaa=1, max_depth=4, flags=4 | 1)
+    assert_radiance_close(fb, fa, name + " no-jitter", outliers=1e-3)
+    assert_stats_close(sb, sa, name + " no-jitter")
+
+
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("integrator,depth", [("path", 1), ("direct", 5), ("path", 5)])
 def test_per_sample_radiance_and_counters(oracle_api, gpu_api, name, integrator, depth):

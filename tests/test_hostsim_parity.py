@@ -29,6 +29,21 @@ def test_per_sample_radiance_and_counters(oracle_api, hostsim_api, name, integra
     assert_stats_close(sb, sa, f"{name} {integrator} depth {depth}")
 
 
+@pytest.mark.parametrize("name", ["edge_mesh", "edge_single", "cornell"])
+def test_axis_aligned_rays_no_jitter(oracle_api, hostsim_api, name):
+    """PBRS_FLAG_NO_JITTER: the centre column / row rays have exactly-zero direction components,
+    i.e. infinite reciprocals and 0/0 slabs -- the walker's exact-division path."""
+    sd = SMALL_SCENES[name]()
+    ho, hh = sd.realize(oracle_api), sd.realize(hostsim_api)
+    a = ho.render_ids(0, msaa=1, flags=4)
+    b = hh.render_ids(0, msaa=1, flags=4)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bits_equal(a[2], b[2]).all()
+    fa, sa = ho.render_samples(integrator="path", msaa=1, max_depth=4, flags=4 | 1)
+    fb, sb = hh.render_samples(integrator="path", msaa=1, max_depth=4, flags=4 | 1)
+    assert_radiance_close(fb, fa, name + " no-jitter", outliers=1e-3)
+    assert_stats_close(sb, sa, name + " no-jitter")
+
+
 def test_film_and_splits(oracle_api, hostsim_api):
     sd = SMALL_SCENES["cornell"]()
     ho, hh = sd.realize(oracle_api), sd.realize(hostsim_api)

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 // phase 2 (one leaf or unwind) and, whenever enough lanes have run dry, draws the next rays from
 // the queue with a single atomicAdd on the launch's work cursor.
 #ifndef PBRS_REFILL_IDLE_LANES
-#define PBRS_REFILL_IDLE_LANES 24
+#define PBRS_REFILL_IDLE_LANES 20
 #endif
 constexpr int kRefillIdleLanes = PBRS_REFILL_IDLE_LANES;  // refill as soon as this many lanes are idle
 #ifndef PBRS_LEAF_VOTE

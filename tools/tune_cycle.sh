@@ -1,4 +1,4 @@
-for lib in libpbrs_gpu_p1.so libpbrs_gpu_p2.so libpbrs_gpu.so libpbrs_gpu_p4.so; do
+for lib in libpbrs_gpu.so libpbrs_gpu_v6r24.so libpbrs_gpu_v10r24.so libpbrs_gpu_v8r20.so libpbrs_gpu_v8r28.so libpbrs_gpu_v12r28.so; do
 export PBRS_GPU_LIB=$PWD/pbrs_b200/lib/$lib
 for w in c3 c4 c5; do sc=1.0; [ $w = c4 ] && sc=0.25;  [ $w = c5 ] && sc=0.125; python bench.py --workload $w --steps 1 --warmup 1 --no-cpu --frame-scale $sc > gpurun_out/t.json 2> gpurun_out/t.err; tail -2 gpurun_out/t.err; python -c "
-import json,sys; d=json.load(open('gpurun_out/t.json')); print('$lib $w', round(d['value'],1), 'Msamples/s', round(d['mrays_per_s'],1), 'Mrays/s frac', round(d['roofline']['frac'],3), {k:round(v,2) for k,v in d['stages_ms'].items()})"; done; done
+import json,sys; d=json.load(open('gpurun_out/t.json')); print('$lib $w', round(d['value'],1), 'Msamples/s frac', round(d['roofline']['frac'],3), {k[3:]:round(v,1) for k,v in d['stages_ms'].items()})"; done; done

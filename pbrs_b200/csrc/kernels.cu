@@ -20,6 +20,9 @@ namespace pbrs {
 namespace {
 
 constexpr int kThreads = 128;
+#ifndef PBRS_LANES
+#define PBRS_LANES 2
+#endif
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
@@ -297,10 +300,15 @@ void size_shade(Grid &g, int sms) {
 
 struct Workspace {
     int device = -1;
+    // Two lanes: consecutive batches alternate between two sets of path buffers on two streams, so
+    // that the tail of one batch's persistent kernels (a few straggling warps) overlaps the next
+    // batch's work instead of leaving SMs idle.
     uint32_t capacity = 0;
-    char *slab = nullptr;
-    size_t slab_bytes = 0;
-    PathBuffers pb{};
+    int n_lanes = 0;
+    char *slab[2] = {nullptr, nullptr};
+    PathBuffers pb[2]{};
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     uint32_t *counts = nullptr;
     uint32_t counts_cap = 0;   // in batches
     uint32_t *tiles = nullptr;
@@ -315,7 +323,10 @@ struct Workspace {
 
 void workspace_free(Workspace *w) {
     if (!w) return;
-    if (w->slab) cudaFree(w->slab);
+    for (auto &p : w->slab) if (p) cudaFree(p);
+    for (auto &q : w->lane_stream) if (q) cudaStreamDestroy(q);
+    if (w->fork_ev) cudaEventDestroy(w->fork_ev);
+    for (auto &e : w->join_ev) if (e) cudaEventDestroy(e);
     if (w->counts) cudaFree(w->counts);
     if (w->tiles) cudaFree(w->tiles);
     if (w->stats) cudaFree(w->stats);
@@ -324,7 +335,7 @@ void workspace_free(Workspace *w) {
     delete w;
 }
 
-static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint32_t n_batches, uint32_t n_tiles) {
+static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int n_lanes, uint32_t n_batches, uint32_t n_tiles) {
     if (!wp) wp = new Workspace();
     Workspace &w = *wp;
     if (w.device != device) {
@@ -345,27 +356,34 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint
     }
     if (!w.ev[0]) { CK(cudaEventCreate(&w.ev[0])); CK(cudaEventCreate(&w.ev[1])); }
     if (!w.stats) CK(cudaMalloc(&w.stats, sizeof(unsigned long long) * kStatCount));
-    if (w.capacity < capacity) {
-        if (w.slab) { cudaFree(w.slab); w.slab = nullptr; }
+    if (!w.lane_stream[0]) {
+        for (int l = 0; l < 2; ++l) { CK(cudaStreamCreateWithFlags(&w.lane_stream[l], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.join_ev[l], cudaEventDisableTiming)); }
+        CK(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
+    }
+    if (w.capacity < capacity || w.n_lanes < n_lanes) {
+        for (auto &p : w.slab) if (p) { cudaFree(p); p = nullptr; }
+        w.capacity = 0; w.n_lanes = 0;
         // 13 x 16-byte arrays + 1 float + (3 + PBRS_NUM_CLS) queues per path slot
         size_t per = 13 * sizeof(f4) + sizeof(float) + (3 + PBRS_NUM_CLS) * sizeof(uint32_t);
         size_t bytes = per * (size_t)capacity + 4096;
-        cudaError_t e = cudaMalloc(&w.slab, bytes);
-        if (e != cudaSuccess) { set_error("path workspace: out of device memory"); w.capacity = 0; return PBRS_ERR_OOM; }
-        w.slab_bytes = bytes;
+        for (int l = 0; l < n_lanes; ++l) {
+            cudaError_t e = cudaMalloc(&w.slab[l], bytes);
+            if (e != cudaSuccess) { cudaGetLastError(); set_error("path workspace: out of device memory"); return PBRS_ERR_OOM; }
+            char *p = w.slab[l];
+            auto take = [&](size_t elem) { char *q = p; p += elem * (size_t)capacity; return q; };
+            PathBuffers &pb = w.pb[l];
+            pb.ray_o = (f4 *)take(16); pb.ray_d = (f4 *)take(16); pb.hit = (u4 *)take(16); pb.beta = (f4 *)take(16);
+            pb.rad = (f4 *)take(16); pb.aux = (f4 *)take(16);
+            pb.sh_o1 = (f4 *)take(16); pb.sh_d1 = (f4 *)take(16); pb.sh_o2 = (f4 *)take(16); pb.sh_d2 = (f4 *)take(16);
+            pb.sh_c = (f4 *)take(16); pb.sh_b = (f4 *)take(16);
+            (void)take(16);  // spare
+            pb.sh_m = (float *)take(4);
+            pb.queue[0] = (uint32_t *)take(4); pb.queue[1] = (uint32_t *)take(4); pb.shadow_queue = (uint32_t *)take(4);
+            for (int c = 0; c < PBRS_NUM_CLS; ++c) pb.cls_queue[c] = (uint32_t *)take(4);
+            pb.capacity = capacity;
+        }
         w.capacity = capacity;
-        char *p = w.slab;
-        auto take = [&](size_t elem) { char *q = p; p += elem * (size_t)capacity; return q; };
-        PathBuffers &pb = w.pb;
-        pb.ray_o = (f4 *)take(16); pb.ray_d = (f4 *)take(16); pb.hit = (u4 *)take(16); pb.beta = (f4 *)take(16);
-        pb.rad = (f4 *)take(16); pb.aux = (f4 *)take(16);
-        pb.sh_o1 = (f4 *)take(16); pb.sh_d1 = (f4 *)take(16); pb.sh_o2 = (f4 *)take(16); pb.sh_d2 = (f4 *)take(16);
-        pb.sh_c = (f4 *)take(16); pb.sh_b = (f4 *)take(16);
-        (void)take(16);  // spare
-        pb.sh_m = (float *)take(4);
-        pb.queue[0] = (uint32_t *)take(4); pb.queue[1] = (uint32_t *)take(4); pb.shadow_queue = (uint32_t *)take(4);
-        for (int c = 0; c < PBRS_NUM_CLS; ++c) pb.cls_queue[c] = (uint32_t *)take(4);
-        pb.capacity = capacity;
+        w.n_lanes = n_lanes;
     }
     if (w.counts_cap < n_batches) {
         if (w.counts) cudaFree(w.counts);
@@ -377,7 +395,7 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, uint
         CK(cudaMalloc(&w.tiles, sizeof(uint32_t) * (size_t)n_tiles));
         w.tiles_cap = n_tiles;
     }
-    w.pb.stats = w.stats;
+    for (auto &pb : w.pb) pb.stats = w.stats;
     return 0;
 }
 
@@ -428,13 +446,15 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     const uint32_t ppb = std::max<uint32_t>(1u, capacity / std::max(fp.spp_r, 1u));  // pixels per batch
     const uint32_t n_batches = fp.spp_r == 0 ? 0 : (uint32_t)((total_pixels + ppb - 1) / ppb);
 
-    Workspace *&wp = s.workspace;
-    int rc = workspace_prepare(wp, s.device, capacity, std::max(n_batches, 1u), std::max(fp.n_tiles, 1u));
-    if (rc < 0) return rc;
-    Workspace &w = *wp;
-    PathBuffers pb = w.pb;
     const bool count_trav = (o.flags & PBRS_FLAG_COUNT_TRAVERSAL) != 0;
     const bool want_stats = st != nullptr;
+    // per-stage timing needs one in-order stream; everything else pipelines batches over two lanes
+    const int n_lanes = (n_batches >= 2 && !(want_stats && (o.flags & PBRS_FLAG_TIME_STAGES))) ? PBRS_LANES : 1;
+    Workspace *&wp = s.workspace;
+    int rc = workspace_prepare(wp, s.device, capacity, n_lanes, std::max(n_batches, 1u), std::max(fp.n_tiles, 1u));
+    if (rc < 0) return rc;
+    Workspace &w = *wp;
+    cudaStream_t const caller_stream = stream;
 
     if (fp.n_tiles) CK(cudaMemcpyAsync(w.tiles, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, stream));
     fp.tiles = w.tiles;
@@ -463,7 +483,13 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         return 0;
     };
     mark(-1);
+    if (n_lanes > 1) {
+        CK(cudaEventRecord(w.fork_ev, caller_stream));
+        for (int l = 0; l < n_lanes; ++l) CK(cudaStreamWaitEvent(w.lane_stream[l], w.fork_ev, 0));
+    }
     for (uint32_t b = 0; b < n_batches; ++b) {
+        PathBuffers pb = w.pb[b % (uint32_t)n_lanes];
+        stream = n_lanes > 1 ? w.lane_stream[b % (uint32_t)n_lanes] : caller_stream;
         BatchParams bp;
         bp.first_pixel = b * ppb;
         bp.n_pixels = (uint32_t)std::min<uint64_t>(ppb, total_pixels - (uint64_t)b * ppb);
@@ -496,6 +522,9 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
             if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; mark(T_ACC); }
         }
     }
+    stream = caller_stream;
+    if (n_lanes > 1)
+        for (int l = 0; l < n_lanes; ++l) { CK(cudaEventRecord(w.join_ev[l], w.lane_stream[l])); CK(cudaStreamWaitEvent(caller_stream, w.join_ev[l], 0)); }
     CK(cudaGetLastError());
     if (want_stats) {
         CK(cudaEventRecord(w.ev[1], stream));

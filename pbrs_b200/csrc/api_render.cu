@@ -70,7 +70,7 @@ int pbrs_render(const pbrs_scene *s, const pbrs_render_opts *o, float *out_rgb, 
     if (rc < 0) return rc;
     e = cudaMemcpy(out_rgb, impl.film, bytes, cudaMemcpyDeviceToHost);  // synchronises the frame
     if (e != cudaSuccess) return cuda_fail(e, "film copy");
-    return 0;
+    return check_last_frame(impl);
 }
 
 int pbrs_render_ids(const pbrs_scene *s, const pbrs_render_opts *o, uint32_t sample_index, uint32_t *out_inst, uint32_t *out_prim, float *out_t) {
@@ -95,7 +95,7 @@ int pbrs_render_ids(const pbrs_scene *s, const pbrs_render_opts *o, uint32_t sam
     if (out_prim && (e = cudaMemcpy(out_prim, bp.p, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "ids copy");
     if (out_t && (e = cudaMemcpy(out_t, bt.p, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "ids copy");
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(e, "render_ids");
-    return 0;
+    return check_last_frame(impl);
 }
 
 int pbrs_render_samples(const pbrs_scene *s, const pbrs_render_opts *o, float *out_rgb_samples, pbrs_stats *st) {
@@ -115,7 +115,7 @@ int pbrs_render_samples(const pbrs_scene *s, const pbrs_render_opts *o, float *o
     rc = render_frame(impl, *o, tg, nullptr, st);
     if (rc < 0) return rc;
     if ((e = cudaMemcpy(out_rgb_samples, buf.p, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "samples copy");
-    return 0;
+    return check_last_frame(impl);
 }
 
 }  // extern "C"

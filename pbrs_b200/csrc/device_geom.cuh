@@ -1,5 +1,5 @@
-// Ray / box / triangle / sphere arithmetic and the two BVH walks (closest hit, any hit) over the
-// flattened records of records.h.
+// Ray / box / triangle / sphere arithmetic over the flattened records of records.h (the BVH walks
+// that use it are in device_walk.cuh).
 //
 // Parity contract (DESIGN.md "Traversal"): the walks visit the same boxes, in the same order and
 // with the same ray extent as the reference's recursive/stack walks, so that the integer outcome
@@ -135,7 +135,7 @@ PB_DEV TriVerts load_tri(const TriRec *t) {
 
 struct MeshHead {
     float bmin[3], bmax[3];
-    uint32_t node_base, tri_base, n_tris, root_is_leaf, vert_base, idx_base;
+    uint32_t node_base, tri_base, n_tris, root_is_leaf;
 };
 PB_DEV MeshHead load_mesh_head(const MeshRec *m) {
     const char *b = reinterpret_cast<const char *>(m);
@@ -143,7 +143,7 @@ PB_DEV MeshHead load_mesh_head(const MeshRec *m) {
     MeshHead h;
     h.bmin[0] = a.x; h.bmin[1] = a.y; h.bmin[2] = a.z; h.bmax[0] = a.w; h.bmax[1] = c.x; h.bmax[2] = c.y;
     h.node_base = f2u(c.z); h.tri_base = f2u(c.w);
-    h.n_tris = f2u(d.x); h.root_is_leaf = f2u(d.y); h.vert_base = f2u(d.z); h.idx_base = f2u(d.w);
+    h.n_tris = f2u(d.x); h.root_is_leaf = f2u(d.y);
     return h;
 }
 
@@ -155,26 +155,22 @@ struct MeshHit {
     vec3 pos, normal, dpdu;
     float t, u, v;
 };
-PB_DEV bool mesh_tri_shade(const DeviceScene &sc, const MeshHead &m, const TriVerts &tv, const Ray &r, MeshHit &out,
+PB_DEV bool mesh_tri_shade(const DeviceScene &sc, uint32_t tri_index, const TriVerts &tv, const Ray &r, MeshHit &out,
                            Diag &dg) {
     TriHit h;
     if (!tri_intersect(tv.p0, tv.p1, tv.p2, r, h, dg)) return false;
     float b0 = 1.0f - h.b1 - h.b2, b1 = h.b1, b2 = h.b2;
     vec3 hit_by_uv = tv.p0 + (tv.p1 - tv.p0) * b1 + (tv.p2 - tv.p0) * b2;
     if (!(len2(hit_by_uv - h.pos) < 1e-6f)) flag(dg, P_MESH_UV);
-    // (i, k, j) = index_triple: vertex 1 of the record is idx.2, vertex 2 is idx.1 (blas.rs:162)
-    const uint32_t *ix = sc.tri_idx + 3u * (m.idx_base + tv.orig);
-    uint32_t i = m.vert_base + ld_u32(ix), k = m.vert_base + ld_u32(ix + 1), j = m.vert_base + ld_u32(ix + 2);
-    const float *N = sc.vert_normals, *UV = sc.vert_uvs;
-    vec3 n0 = mk(ld_f32(N + 3 * i), ld_f32(N + 3 * i + 1), ld_f32(N + 3 * i + 2));
-    vec3 n1 = mk(ld_f32(N + 3 * j), ld_f32(N + 3 * j + 1), ld_f32(N + 3 * j + 2));
-    vec3 n2 = mk(ld_f32(N + 3 * k), ld_f32(N + 3 * k + 1), ld_f32(N + 3 * k + 2));
+    // the triangle's shading record: normals and uvs of its three vertices in TriRec order
+    // ((i, k, j) = index_triple: vertex 1 is idx.2, vertex 2 is idx.1, blas.rs:162)
+    const char *sr = reinterpret_cast<const char *>(sc.tri_shade + tri_index);
+    const f4 s0 = ld16(sr), s1 = ld16(sr + 16), s2 = ld16(sr + 32), s3 = ld16(sr + 48);
+    vec3 n0 = mk(s0.x, s0.y, s0.z), n1 = mk(s0.w, s1.x, s1.y), n2 = mk(s1.z, s1.w, s2.x);
+    const float ui = s2.y, vi = s2.z, uj = s2.w, vj = s3.x, uk = s3.y, vk = s3.z;
     vec3 bn;
     if (!try_hat(bary_lerp(n0, n1, n2, b0, b1), bn)) bn = h.normal;
     bn = facing(bn, r.d);
-    float ui = ld_f32(UV + 2 * i), vi = ld_f32(UV + 2 * i + 1);
-    float uj = ld_f32(UV + 2 * j), vj = ld_f32(UV + 2 * j + 1);
-    float uk = ld_f32(UV + 2 * k), vk = ld_f32(UV + 2 * k + 1);
     float uu = bary_lerp(ui, uj, uk, b0, b1);
     float vv = bary_lerp(vi, vj, vk, b0, b1);
     float u1 = uj - ui, v1 = vj - vi;
@@ -266,319 +262,11 @@ PB_DEV Ray to_object(const InstTravRec *it, const Ray &r, uint32_t &shape_kind, 
 }
 
 #define PBRS_LEAF_BIT 0x80000000u
-#define PBRS_BLAS_STACK 64
-#define PBRS_TLAS_STACK 192
 
-struct NodeView {
-    float lt, lme, rt, rme;  // (t_low, min_el) of the left / right child box
-    uint32_t lref, rref;     // child refs with PBRS_LEAF_BIT
-    uint32_t axis;
-};
-PB_DEV NodeView expand_node(const NodeRec *n, const Ray &r) {
-    const char *b = reinterpret_cast<const char *>(n);
-    f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32), q3 = ld16(b + 48);
-    NodeView v;
-    slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, v.lt, v.lme);
-    slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, v.rt, v.rme);
-    uint32_t meta = f2u(q3.z);
-    v.lref = f2u(q3.x) | ((meta & PBRS_NODE_LEFT_LEAF) ? PBRS_LEAF_BIT : 0u);
-    v.rref = f2u(q3.y) | ((meta & PBRS_NODE_RIGHT_LEAF) ? PBRS_LEAF_BIT : 0u);
-    v.axis = meta & 3u;
-    return v;
-}
-
-// ---------------------------------------------------------------------------------------------
-// BLAS closest hit, shape/src/blas.rs:422-476.  `r` is the object-space ray carrying the extent
-// the TLAS handed in; that extent only prunes the root (Q17): after the first pop the walk's
-// extent is its own best hit.  Returns the local best (t, triangle record index).
-// ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-PB_DEV bool blas_leaf_closest(const DeviceScene &sc, const MeshHead &m, uint32_t first, const Ray &ray,
-                              float &best_t, uint32_t &best_tri, Diag &dg, TravCount &tc) {
-    bool any = false;
-    uint32_t s = m.tri_base + first;
-    while (true) {
-        TriVerts tv = load_tri(sc.tris + s);
-        if (COUNT) tc.tris++;
-        float t;
-        bool hit;
-        if (tv.flags & PBRS_TRI_CHECK_SHADING) {
-            MeshHit mh;
-            hit = mesh_tri_shade(sc, m, tv, ray, mh, dg);
-            t = mh.t;
-        } else {
-            TriHit h;
-            hit = tri_intersect(tv.p0, tv.p1, tv.p2, ray, h, dg);
-            t = h.t;
-        }
-        if (hit && t < best_t) { best_t = t; best_tri = s; any = true; }
-        if (tv.flags & PBRS_TRI_LAST_IN_LEAF) break;
-        ++s;
-    }
-    return any;
-}
-
-template <bool COUNT>
-PB_DEV bool blas_closest(const DeviceScene &sc, uint32_t mesh_index, Ray ray, float &out_t, uint32_t &out_tri, Diag &dg,
-                         TravCount &tc) {
-    const MeshRec *mrec = sc.meshes + mesh_index;
-    MeshHead m = load_mesh_head(mrec);
-    float tl, me;
-    slab(m.bmin[0], m.bmin[1], m.bmin[2], m.bmax[0], m.bmax[1], m.bmax[2], ray, tl, me);
-    if (!box_pass(tl, me, ray.t_max)) return false;  // blas.rs:428 and the root's own pop (:441)
-    float best_t = PB_INF;
-    uint32_t best_tri = 0xFFFFFFFFu;
-    if (m.root_is_leaf) {
-        // the root leaf's primitives see the incoming extent (the clone of `r`)
-        blas_leaf_closest<COUNT>(sc, m, 0u, ray, best_t, best_tri, dg, tc);
-        out_t = best_t; out_tri = best_tri;
-        return best_t < PB_INF;
-    }
-    uint32_t st_ref[PBRS_BLAS_STACK];
-    float st_tl[PBRS_BLAS_STACK];
-    int sp = 0;
-    uint32_t cur = 0u;  // inner node, mesh-relative
-    const NodeRec *nodes = sc.blas_nodes + m.node_base;
-    ray.t_max = best_t;  // blas.rs:468 after the root pop
-    while (true) {
-        // `cur` is an inner node that was popped and passed its box test: expand it
-        if (COUNT) tc.nodes++;
-        NodeView v = expand_node(nodes + cur, ray);
-        bool lp = box_pass(v.lt, v.lme, ray.t_max), rp = box_pass(v.rt, v.rme, ray.t_max);
-        // blas.rs:456-466: near = left iff dir[axis] > 0; far is pushed first, near popped next
-        bool left_near = comp(ray.d, (int)v.axis) > 0.0f;
-        uint32_t near_ref = left_near ? v.lref : v.rref, far_ref = left_near ? v.rref : v.lref;
-        bool near_pass = left_near ? lp : rp, far_pass = left_near ? rp : lp;
-        float far_tl = left_near ? v.rt : v.lt;
-        if (far_pass) {
-            if (sp < PBRS_BLAS_STACK) { st_ref[sp] = far_ref; st_tl[sp] = far_tl; ++sp; }
-            else flag(dg, P_STACK);
-        }
-        uint32_t next = 0xFFFFFFFFu;
-        if (near_pass) next = near_ref;
-        while (true) {
-            if (next == 0xFFFFFFFFu) {
-                // pop; the box test at pop time (:441) reduces to t_low <= current extent
-                bool got = false;
-                while (sp > 0) {
-                    --sp;
-                    if (st_tl[sp] <= ray.t_max) { next = st_ref[sp]; got = true; break; }
-                }
-                if (!got) {
-                    out_t = best_t; out_tri = best_tri;
-                    return best_t < PB_INF;
-                }
-            }
-            if (next & PBRS_LEAF_BIT) {
-                blas_leaf_closest<COUNT>(sc, m, next & ~PBRS_LEAF_BIT, ray, best_t, best_tri, dg, tc);
-                ray.t_max = best_t;  // :468
-                next = 0xFFFFFFFFu;
-                continue;
-            }
-            cur = next;
-            break;
-        }
-    }
-}
-
-// BLAS any hit, shape/src/blas.rs:478-495: depth-first, left before right, the ray's own extent.
-template <bool COUNT>
-PB_DEV bool blas_any(const DeviceScene &sc, uint32_t mesh_index, const Ray &ray, Diag &dg, TravCount &tc) {
-    const MeshRec *mrec = sc.meshes + mesh_index;
-    MeshHead m = load_mesh_head(mrec);
-    float tl, me;
-    slab(m.bmin[0], m.bmin[1], m.bmin[2], m.bmax[0], m.bmax[1], m.bmax[2], ray, tl, me);
-    if (!box_pass(tl, me, ray.t_max)) return false;
-    uint32_t st_ref[PBRS_BLAS_STACK];
-    int sp = 0;
-    uint32_t next = m.root_is_leaf ? PBRS_LEAF_BIT : 0u;
-    const NodeRec *nodes = sc.blas_nodes + m.node_base;
-    while (true) {
-        if (next & PBRS_LEAF_BIT) {
-            uint32_t s = m.tri_base + (next & ~PBRS_LEAF_BIT);
-            while (true) {
-                TriVerts tv = load_tri(sc.tris + s);
-                if (COUNT) tc.tris++;
-                if (tri_occludes(tv.p0, tv.p1, tv.p2, ray, dg)) return true;
-                if (tv.flags & PBRS_TRI_LAST_IN_LEAF) break;
-                ++s;
-            }
-        } else {
-            if (COUNT) tc.nodes++;
-            NodeView v = expand_node(nodes + next, ray);
-            bool lp = box_pass(v.lt, v.lme, ray.t_max), rp = box_pass(v.rt, v.rme, ray.t_max);
-            if (lp) {
-                if (rp) {
-                    if (sp < PBRS_BLAS_STACK) st_ref[sp++] = v.rref;
-                    else flag(dg, P_STACK);
-                }
-                next = v.lref;
-                continue;
-            }
-            if (rp) { next = v.rref; continue; }
-        }
-        if (sp == 0) return false;
-        next = st_ref[--sp];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Instance leaves.  tlas/src/instance.rs:50-72.
-// ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-PB_DEV bool instance_closest(const DeviceScene &sc, uint32_t inst, const Ray &ray, float &t, uint32_t &tri, Diag &dg,
-                             TravCount &tc) {
-    if (COUNT) tc.insts++;
-    uint32_t kind, index;
-    Ray o = to_object(sc.inst_trav + inst, ray, kind, index);
-    if (!(len2(o.d) > 1e-3f)) flag(dg, P_MISC);
-    if (kind == PBRS_SHAPE_SPHERE) {
-        if (COUNT) tc.spheres++;
-        f4 s = ld16(sc.spheres + index);
-        tri = 0u;
-        return sphere_hit_t(mk(s.x, s.y, s.z), s.w, o, t);
-    }
-    return blas_closest<COUNT>(sc, index, o, t, tri, dg, tc);
-}
-template <bool COUNT>
-PB_DEV bool instance_any(const DeviceScene &sc, uint32_t inst, const Ray &ray, Diag &dg, TravCount &tc) {
-    if (COUNT) tc.insts++;
-    uint32_t kind, index;
-    Ray o = to_object(sc.inst_trav + inst, ray, kind, index);
-    if (!(len2(o.d) > 1e-6f)) flag(dg, P_MISC);
-    if (kind == PBRS_SHAPE_SPHERE) {
-        if (COUNT) tc.spheres++;
-        f4 s = ld16(sc.spheres + index);
-        return sphere_occludes(mk(s.x, s.y, s.z), s.w, o);
-    }
-    return blas_any<COUNT>(sc, index, o, dg, tc);
-}
-
-// ---------------------------------------------------------------------------------------------
-// TLAS closest hit, tlas/src/bvh.rs:77-103, restated without recursion.
-//
-//   visit(n): box(n) with the CURRENT extent, else None
-//             leaf -> instance hit
-//             inner -> l = visit(left); if l { ray.t_max = l.t }; r = visit(right);
-//                      pick: l if l.t < r.t else r
-// The fold of `pick` over the leaves is "smallest t, right-most on ties", so a running best
-// updated with `<=` reproduces the winner.  The extent, however, is NOT the running best: it is
-// the t of the most recently completed left subtree that hit, which (Q17: a mesh walk ignores the
-// incoming extent below its root) may even grow.  To reproduce it, the stack carries, besides
-// pending right children (with their slab values, re-tested against the extent of the moment),
-// the value of a finished left subtree waiting to be combined with its sibling's.
-//   entry kinds:  [me][tl][ref | T_RIGHT]      right child of a node whose left subtree is running
-//                 [lv][T_COMBINE]              left value waiting for the right subtree's value
-// ---------------------------------------------------------------------------------------------
+// The winner of a closest-hit walk: t, instance id, triangle record index (0 for spheres).
 struct Hit {
     float t;
     uint32_t inst, tri;
 };
-#define PBRS_T_COMBINE 0x40000000u
-#define PBRS_T_MASK 0x40000000u
-
-template <bool COUNT>
-PB_DEV bool tlas_closest(const DeviceScene &sc, Ray &ray, Hit &best, Diag &dg, TravCount &tc) {
-    best.t = PB_INF; best.inst = 0xFFFFFFFFu; best.tri = 0xFFFFFFFFu;
-    bool found = false;
-    float tl, me;
-    slab(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], ray, tl, me);
-    if (!box_pass(tl, me, ray.t_max)) return false;
-    if (sc.tlas_root_is_leaf) {
-        float t; uint32_t tri;
-        if (instance_closest<COUNT>(sc, 0u, ray, t, tri, dg, tc)) { best.t = t; best.inst = 0u; best.tri = tri; return true; }
-        return false;
-    }
-    uint32_t st[PBRS_TLAS_STACK];
-    int sp = 0;
-    uint32_t cur = 0u;  // inner node to expand (its box already passed)
-    float ret = PB_INF; // value of the subtree that just completed
-    while (true) {
-        // ---- expand inner node `cur`, descend into its left child ----
-        if (COUNT) tc.nodes++;
-        NodeView v = expand_node(sc.tlas_nodes + cur, ray);
-        // the right child can only ever pass if its slabs overlap at all (NaN min_el: keep it)
-        if (!(v.rt > v.rme)) {
-            if (sp + 3 <= PBRS_TLAS_STACK) { st[sp] = f2u(v.rme); st[sp + 1] = f2u(v.rt); st[sp + 2] = v.rref; sp += 3; }
-            else flag(dg, P_STACK);
-        }
-        uint32_t visit = box_pass(v.lt, v.lme, ray.t_max) ? v.lref : 0xFFFFFFFFu;
-        bool descend = false;
-        while (true) {
-            // ---- visit `visit` (box already passed) or produce None ----
-            if (visit == 0xFFFFFFFFu) {
-                ret = PB_INF;
-            } else if (visit & PBRS_LEAF_BIT) {
-                uint32_t inst = visit & ~PBRS_LEAF_BIT;
-                float t; uint32_t tri;
-                if (instance_closest<COUNT>(sc, inst, ray, t, tri, dg, tc)) {
-                    ret = t;
-                    if (t <= best.t) { best.t = t; best.inst = inst; best.tri = tri; }
-                    found = true;
-                } else {
-                    ret = PB_INF;
-                }
-            } else {
-                cur = visit;
-                descend = true;
-                break;
-            }
-            // ---- a subtree completed with value `ret`: unwind ----
-            bool resumed = false;
-            while (sp > 0) {
-                uint32_t top = st[sp - 1];
-                if (top == PBRS_T_COMBINE) {
-                    float lv = u2f(st[sp - 2]);
-                    sp -= 2;
-                    ret = (lv < ret) ? lv : ret;  // pick(l, r).t
-                    continue;
-                }
-                // right child pending: the subtree that just finished was its left sibling
-                float r_tl = u2f(st[sp - 2]), r_me = u2f(st[sp - 3]);
-                sp -= 3;
-                if (ret < PB_INF) {
-                    ray.t_max = ret;  // ray.set_extent(isect.ray_t)
-                    st[sp] = f2u(ret); st[sp + 1] = PBRS_T_COMBINE; sp += 2;  // room: we just freed 3
-                }
-                visit = box_pass(r_tl, r_me, ray.t_max) ? top : 0xFFFFFFFFu;
-                resumed = true;
-                break;
-            }
-            if (!resumed) return found;
-        }
-        if (!descend) return found;
-    }
-}
-
-// TLAS any hit, tlas/src/bvh.rs:105-113.
-template <bool COUNT>
-PB_DEV bool tlas_any(const DeviceScene &sc, const Ray &ray, Diag &dg, TravCount &tc) {
-    float tl, me;
-    slab(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], ray, tl, me);
-    if (!box_pass(tl, me, ray.t_max)) return false;
-    uint32_t st[PBRS_BLAS_STACK];
-    int sp = 0;
-    uint32_t next = sc.tlas_root_is_leaf ? PBRS_LEAF_BIT : 0u;
-    while (true) {
-        if (next & PBRS_LEAF_BIT) {
-            if (instance_any<COUNT>(sc, next & ~PBRS_LEAF_BIT, ray, dg, tc)) return true;
-        } else {
-            if (COUNT) tc.nodes++;
-            NodeView v = expand_node(sc.tlas_nodes + next, ray);
-            bool lp = box_pass(v.lt, v.lme, ray.t_max), rp = box_pass(v.rt, v.rme, ray.t_max);
-            if (lp) {
-                if (rp) {
-                    if (sp < PBRS_BLAS_STACK) st[sp++] = v.rref;
-                    else flag(dg, P_STACK);
-                }
-                next = v.lref;
-                continue;
-            }
-            if (rp) { next = v.rref; continue; }
-        }
-        if (sp == 0) return false;
-        next = st[--sp];
-    }
-}
 
 }  // namespace pbrs

@@ -200,11 +200,10 @@ PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32
         f4 s = ld16(sc.spheres + index);
         sphere_intersect(mk(s.x, s.y, s.z), s.w, o, h, dg, f2u(tail.z) != 0u);
     } else {
-        MeshHead m = load_mesh_head(sc.meshes + index);
         TriVerts tv = load_tri(sc.tris + tri);
         MeshHit mh;
         mh.pos = mk(0, 0, 0); mh.normal = mk(0, 0, 1); mh.dpdu = mk(1, 0, 0); mh.t = 0; mh.u = 0; mh.v = 0;
-        if (!mesh_tri_shade(sc, m, tv, o, mh, dg)) flag(dg, P_MISC);
+        if (!mesh_tri_shade(sc, tri, tv, o, mh, dg)) flag(dg, P_MISC);
         h = isect_new(mh.pos, mh.t, mh.u, mh.v, mh.normal, -o.d, dg);
         with_dpdu(h, mh.dpdu, dg);
     }

@@ -265,7 +265,7 @@ struct Walk {
                     bool hit;
                     if (tv.flags & PBRS_TRI_CHECK_SHADING) {
                         MeshHit mh;
-                        hit = mesh_tri_shade(sc, load_mesh_head(sc.meshes + mesh_index), tv, ray, mh, dg);
+                        hit = mesh_tri_shade(sc, s, tv, ray, mh, dg);
                         t = mh.t;
                     } else {
                         TriHit h;

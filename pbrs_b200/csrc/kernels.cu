@@ -399,6 +399,14 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
     return 0;
 }
 
+int check_last_frame(SceneImpl &s) {
+    if (!s.workspace || !s.workspace->stats) return 0;
+    unsigned long long overflow = 0;
+    CK(cudaMemcpy(&overflow, s.workspace->stats + kStatPanic0 + P_STACK, sizeof overflow, cudaMemcpyDeviceToHost));
+    if (overflow) { set_error("a traversal stack overflowed (scene deeper than the commit-time bound allows?)"); return PBRS_ERR_UNSUPPORTED; }
+    return 0;
+}
+
 int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st) {
     if (!s.committed) { set_error("render before pbrs_scene_commit"); return PBRS_ERR_STATE; }
     if (o.msaa == 0) { set_error("msaa must be >= 1"); return PBRS_ERR_INVALID_ARG; }

@@ -48,6 +48,16 @@ static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 #define PBRS_TRI_CHECK_SHADING 1u
 #define PBRS_TRI_LAST_IN_LEAF 2u
 
+// Shading attributes of one triangle, gathered per TRIANGLE (same index as its TriRec) instead of
+// per vertex: one dependent fetch after the hit record instead of three (index triple, then the
+// vertex arrays).  Vertex order as in TriRec: 0 = idx.0, 1 = idx.2, 2 = idx.1.
+struct TriShadeRec {
+    float n0[3], n1[3], n2[3];
+    float uv0[2], uv1[2], uv2[2];
+    float pad;
+};
+static_assert(sizeof(TriShadeRec) == 64, "TriShadeRec must be 64 bytes");
+
 struct SphereRec {
     float c[3];
     float r;
@@ -82,9 +92,7 @@ struct MeshRec {
     uint32_t tri_base;    // first TriRec
     uint32_t n_tris;
     uint32_t root_is_leaf;
-    uint32_t vert_base;   // first vertex in the attribute arrays
-    uint32_t idx_base;    // first triangle in the index array (indexed by TriRec::orig)
-    uint32_t pad[4];
+    uint32_t pad[6];
 };
 static_assert(sizeof(MeshRec) == 64, "MeshRec must be 64 bytes");
 
@@ -161,9 +169,7 @@ struct DeviceScene {
     const InstTravRec *inst_trav;
     const InstShadeRec *inst_shade;
     const MeshRec *meshes;
-    const float *vert_normals;  // 3 per vertex
-    const float *vert_uvs;      // 2 per vertex
-    const uint32_t *tri_idx;    // 3 per triangle, caller order
+    const TriShadeRec *tri_shade;  // per triangle, same index as `tris`
     const MaterialRec *materials;
     const TextureRec *textures;
     const uint32_t *texels;     // RGBA8

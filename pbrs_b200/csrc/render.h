@@ -22,4 +22,8 @@ void workspace_free(Workspace *);
 // Enqueues the whole frame on `stream`; synchronises only when `st` is given.
 int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st);
 
+// After the frame's work has completed on the host side (the caller synchronised): fails loudly
+// if a traversal stack overflowed during the last render_frame on this scene.
+int check_last_frame(SceneImpl &s);
+
 }  // namespace pbrs

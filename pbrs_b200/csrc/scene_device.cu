@@ -75,9 +75,7 @@ int device_upload(SceneImpl &s) {
     if ((rc = upload(d, f.trav, ds.inst_trav)) < 0) return rc;
     if ((rc = upload(d, f.shade, ds.inst_shade)) < 0) return rc;
     if ((rc = upload(d, f.meshes, ds.meshes)) < 0) return rc;
-    if ((rc = upload(d, f.normals, ds.vert_normals)) < 0) return rc;
-    if ((rc = upload(d, f.uvs, ds.vert_uvs)) < 0) return rc;
-    if ((rc = upload(d, f.tri_idx, ds.tri_idx)) < 0) return rc;
+    if ((rc = upload(d, f.tri_shade, ds.tri_shade)) < 0) return rc;
     if ((rc = upload(d, s.materials, ds.materials)) < 0) return rc;
     if ((rc = upload(d, f.textures, ds.textures)) < 0) return rc;
     if ((rc = upload(d, f.texels, ds.texels)) < 0) return rc;

@@ -453,8 +453,8 @@ bool host_tri_may_reject(const HostMesh &m, uint32_t t) { return tri_may_reject(
 // Flattens the host scene into the record arrays of records.h (DESIGN.md "Data layout"): a mesh's
 // inner nodes in preorder, its triangles in leaf order with the (i, k, j) vertex swap applied.
 void flatten_scene(const SceneImpl &s, FlatScene &f) {
-    auto &blas_nodes = f.blas_nodes; auto &tris = f.tris; auto &meshes = f.meshes; auto &normals = f.normals; auto &uvs = f.uvs;
-    auto &tri_idx = f.tri_idx; auto &trav = f.trav; auto &shade = f.shade; auto &textures = f.textures; auto &texels = f.texels;
+    auto &blas_nodes = f.blas_nodes; auto &tris = f.tris; auto &meshes = f.meshes; auto &tri_shade = f.tri_shade;
+    auto &trav = f.trav; auto &shade = f.shade; auto &textures = f.textures; auto &texels = f.texels;
     auto &perlin_vec = f.perlin_vec; auto &perlin_perm = f.perlin_perm;
     // ---- meshes: nodes, triangles, attributes ----
     for (const HostMesh &m : s.meshes) {
@@ -465,12 +465,11 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
         r.tri_base = (uint32_t)tris.size();
         r.n_tris = (uint32_t)(m.idx.size() / 3);
         r.root_is_leaf = m.root_is_leaf ? 1u : 0u;
-        r.vert_base = (uint32_t)(normals.size() / 3);
-        r.idx_base = (uint32_t)(tri_idx.size() / 3);
         meshes.push_back(r);
         blas_nodes.insert(blas_nodes.end(), m.nodes.begin(), m.nodes.end());
         size_t t0 = tris.size();
         tris.resize(t0 + m.order.size());
+        tri_shade.resize(t0 + m.order.size());
         for (size_t q = 0; q < m.order.size(); ++q) {
             uint32_t t = m.order[q];
             // (i, k, j) = index_triple, shape/src/blas.rs:162-163
@@ -480,11 +479,16 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
             tr.orig = t;
             tr.flags = host_tri_may_reject(m, t) ? PBRS_TRI_CHECK_SHADING : 0u;
             tr.pad = 0u;
+            TriShadeRec &sr = tri_shade[t0 + q];
+            const uint32_t v3[3] = {i, j, k};
+            float *nd[3] = {sr.n0, sr.n1, sr.n2}, *ud[3] = {sr.uv0, sr.uv1, sr.uv2};
+            for (int a = 0; a < 3; ++a) {
+                for (int c = 0; c < 3; ++c) nd[a][c] = m.N[3 * v3[a] + c];
+                for (int c = 0; c < 2; ++c) ud[a][c] = m.UV[2 * v3[a] + c];
+            }
+            sr.pad = 0.0f;
         }
         for (uint32_t last : m.leaf_last) tris[t0 + last].flags |= PBRS_TRI_LAST_IN_LEAF;
-        normals.insert(normals.end(), m.N.begin(), m.N.end());
-        uvs.insert(uvs.end(), m.UV.begin(), m.UV.end());
-        tri_idx.insert(tri_idx.end(), m.idx.begin(), m.idx.end());
     }
 
     // ---- instances ----

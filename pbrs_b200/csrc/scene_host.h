@@ -84,8 +84,7 @@ struct FlatScene {
     std::vector<NodeRec> blas_nodes;
     std::vector<TriRec> tris;
     std::vector<MeshRec> meshes;
-    std::vector<float> normals, uvs;
-    std::vector<uint32_t> tri_idx;
+    std::vector<TriShadeRec> tri_shade;
     std::vector<InstTravRec> trav;
     std::vector<InstShadeRec> shade;
     std::vector<TextureRec> textures;

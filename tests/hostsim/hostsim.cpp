@@ -38,7 +38,7 @@ int device_upload(SceneImpl &s) {
     std::memset(&ds, 0, sizeof ds);
     ds.tlas_nodes = s.tlas_nodes.data(); ds.blas_nodes = f.blas_nodes.data(); ds.tris = f.tris.data();
     ds.spheres = s.spheres.data(); ds.inst_trav = f.trav.data(); ds.inst_shade = f.shade.data(); ds.meshes = f.meshes.data();
-    ds.vert_normals = f.normals.data(); ds.vert_uvs = f.uvs.data(); ds.tri_idx = f.tri_idx.data();
+    ds.tri_shade = f.tri_shade.data();
     ds.materials = s.materials.data(); ds.textures = f.textures.data(); ds.texels = f.texels.data();
     ds.perlin_vec = f.perlin_vec.data(); ds.perlin_perm = f.perlin_perm.data();
     ds.delta_lights = s.delta_lights.data(); ds.area_lights = s.area_lights.data();

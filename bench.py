@@ -88,7 +88,7 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -256,7 +256,6 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -297,6 +296,9 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_step = float(te.item()) / args.steps
+
+    # the sampler ran from the warm-up through the timed, roofline and e2e legs (all under load)
+    clk = clocks.stop() if rank == 0 else None
 
     # whole-job counts
     cnt = torch.tensor([st_count["n_samples"], st_count["n_rays_extend"], st_count["n_rays_shadow"]], dtype=torch.float64, device="cuda")

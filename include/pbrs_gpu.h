@@ -102,6 +102,24 @@ int pbrs_scene_add_sphere(pbrs_scene *, const float center[3], float radius);
  * -> shape id */
 int pbrs_scene_add_mesh(pbrs_scene *, const float *P, const float *N, const float *UV,
                         uint32_t nverts, const uint32_t *idx, uint32_t ntris);
+/* ParallelQuad{origin, side_u, side_v} (shape/src/simple.rs:69-103: new_xy / new_xz / new_yz are
+ * spelled out by the caller).  intersect :120-150 (u, v from cross-product norms; the
+ * accurate-vs-coarse assert is counted in would_panic[PBRS_PANIC_QUAD]), occludes :151-163
+ * (reciprocal t, transcribed).  -> shape id */
+int pbrs_scene_add_quad(pbrs_scene *, const float origin[3], const float side_u[3],
+                        const float side_v[3]);
+/* Cuboid::from_points (shape/src/simple.rs:173-181; intersect :343-411, occludes = the box
+ * test :412-415).  -> shape id */
+int pbrs_scene_add_cuboid(pbrs_scene *, const float p0[3], const float p1[3]);
+/* Disk::new(center, normal, radial) (shape/src/simple.rs:42-52: the normal is normalised;
+ * a non-finite radial or |radial . normal| >= 1e-6 is PBRS_ERR_INVALID_ARG where the reference
+ * asserts).  intersect :306-326, occludes :328-332 (ignores the ray extent).  -> shape id */
+int pbrs_scene_add_disk(pbrs_scene *, const float center[3], const float normal[3],
+                        const float radial[3]);
+/* IsoBlas::<Sphere>::build (shape/src/blas.rs:60-69, traversal :263-275): n spheres as
+ * (cx, cy, cz, radius) under one bottom-level BVH.  The primitive id reported for a hit is the
+ * sphere's index in this array.  -> shape id */
+int pbrs_scene_add_sphere_blas(pbrs_scene *, const float *centers_radii, uint32_t n);
 
 /* ---- instances: tlas/src/instance.rs:12-45 ---------------------------------------------- */
 /* fwd/inv are column-major 4x4 (the reference's Mat4 is four column Vec4s, math/src/hcm.rs:477),
@@ -124,6 +142,12 @@ int pbrs_scene_add_area_light_sphere(pbrs_scene *, const float center[3], float 
                                      const float emit[3]);
 int pbrs_scene_add_area_light_triangle(pbrs_scene *, const float p0[3], const float p1[3],
                                        const float p2[3], const float emit[3]);
+/* SamplableShape::Quad / ::Disk (light/src/sample_shape.rs:38-43; sample :257-274,296-309;
+ * pdf_at is the trait default :28-33 over the shape's own intersect). */
+int pbrs_scene_add_area_light_quad(pbrs_scene *, const float origin[3], const float side_u[3],
+                                   const float side_v[3], const float emit[3]);
+int pbrs_scene_add_area_light_disk(pbrs_scene *, const float center[3], const float normal[3],
+                                   const float radial[3], const float emit[3]);
 
 /* ---- environment: scene/src/lib.rs:12-16,96-117; scene/src/preset.rs:25-51 -------------- */
 typedef enum pbrs_env_fn {
@@ -204,6 +228,7 @@ typedef struct pbrs_stats {
 #define PBRS_PANIC_REFRACT 10      /* assert_ge!(cos_theta_i, 0) (hcm.rs:629)                */
 #define PBRS_PANIC_MISC 11
 #define PBRS_PANIC_STACK 12         /* not a reference assert: a traversal stack overflowed    */
+#define PBRS_PANIC_QUAD 13          /* quad accurate_hit vs coarse_hit assert (simple.rs:140-147), Q11 */
 
 /* Renders this rank's share of the frame and returns the film in HOST memory:
  * out_rgb is width*height*3 floats, row-major, row 0 = top (src/main.rs:219-231), already

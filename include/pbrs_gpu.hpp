@@ -187,6 +187,30 @@ struct Perlin {
         auto t = std::make_shared<Texture>(); t->kind = Texture::PerlinK; t->freq = freq; t->rand_vec = std::move(rand_vec);
         t->perm_x = std::move(px); t->perm_y = std::move(py); t->perm_z = std::move(pz); return t;
     }
+    // Perlin::with_freq (texture/src/lib.rs:66-96) with a seeded generator in place of thread_rng:
+    // 256 unit vectors, three permutations built by the same swap loop.
+    static TextureRef with_freq(float freq, uint64_t seed = 0x5EED) {
+        uint64_t state = seed;
+        auto next = [&]() { state = state * 6364136223846793005ull + 1442695040888963407ull; return uint32_t(state >> 33); };
+        std::vector<float> rv(768);
+        for (int i = 0; i < 256; ++i) {
+            float v[3], n2;
+            do {
+                for (float &c : v) c = float(next() & 0xFFFFFF) / 8388608.0f - 1.0f;
+                n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+            } while (n2 > 1.0f || n2 < 1e-6f);
+            float inv = 1.0f / std::sqrt(n2);
+            for (int c = 0; c < 3; ++c) rv[3 * i + c] = v[c] * inv;
+        }
+        auto perm = [&]() {
+            std::vector<uint32_t> p(256);
+            for (uint32_t i = 0; i < 256; ++i) p[i] = i;
+            for (uint32_t i = 0; i < 256; ++i) std::swap(p[next() % 256u], p[i]);
+            return p;
+        };
+        auto px = perm(), py = perm(), pz = perm();
+        return with_tables(freq, std::move(rv), std::move(px), std::move(py), std::move(pz));
+    }
 };
 }  // namespace tex
 
@@ -247,10 +271,11 @@ struct Substrate {
 
 // ---- shapes (shape/src/simple.rs, shape/src/blas.rs) ----------------------------------------
 struct Shape {
-    bool is_sphere = true;
-    Point3 center;
+    enum Kind { SphereK, MeshK, QuadK, CuboidK, DiskK, SphereBlasK } kind = SphereK;
+    Point3 center;                 // sphere / disk centre, quad origin, cuboid corner 0
     float radius = 1.0f;
-    std::vector<float> P, N, UV;
+    Vec3 a{}, b{};                 // quad: side_u, side_v; cuboid: a = corner 1; disk: normal, radial
+    std::vector<float> P, N, UV;   // mesh; sphere BLAS: P holds (cx, cy, cz, r) per sphere
     std::vector<uint32_t> idx;
 };
 using ShapeRef = std::shared_ptr<const Shape>;
@@ -263,13 +288,49 @@ struct TriangleMesh {
     // TriangleMesh::from_soa(positions, normals, uvs, index_triples), shape/src/blas.rs:134-159
     static ShapeRef from_soa(std::vector<float> positions, std::vector<float> normals, std::vector<float> uvs, std::vector<uint32_t> index_triples) {
         auto s = std::make_shared<Shape>();
-        s->is_sphere = false;
+        s->kind = Shape::MeshK;
         const size_t nv = positions.size() / 3;
         if (positions.size() % 3 || index_triples.size() % 3 || index_triples.empty()) throw Error(PBRS_ERR_INVALID_ARG, "TriangleMesh::from_soa: bad array sizes");
         if (normals.empty()) normals.assign(nv * 3, 0.0f);
         if (uvs.empty()) uvs.assign(nv * 2, 0.0f);
         if (normals.size() != nv * 3 || uvs.size() != nv * 2) throw Error(PBRS_ERR_INVALID_ARG, "TriangleMesh::from_soa: attribute sizes");
         s->P = std::move(positions); s->N = std::move(normals); s->UV = std::move(uvs); s->idx = std::move(index_triples);
+        return s;
+    }
+};
+// shape/src/simple.rs:69-103
+struct ParallelQuad {
+    Point3 origin;
+    Vec3 side_u, side_v;
+    static ParallelQuad new_xy(std::pair<float, float> x, std::pair<float, float> y, float z) {
+        return {{x.first, y.first, z}, {x.second - x.first, 0.0f, 0.0f}, {0.0f, y.second - y.first, 0.0f}};
+    }
+    static ParallelQuad new_xz(std::pair<float, float> x, float y, std::pair<float, float> z) {
+        return {{x.first, y, z.first}, {x.second - x.first, 0.0f, 0.0f}, {0.0f, 0.0f, z.second - z.first}};
+    }
+    static ParallelQuad new_yz(float x, std::pair<float, float> y, std::pair<float, float> z) {
+        return {{x, y.first, z.first}, {0.0f, 0.0f, z.second - z.first}, {0.0f, y.second - y.first, 0.0f}};
+    }
+    operator ShapeRef() const { auto s = std::make_shared<Shape>(); s->kind = Shape::QuadK; s->center = origin; s->a = side_u; s->b = side_v; return s; }
+};
+// shape/src/simple.rs:166-182
+struct Cuboid {
+    static ShapeRef from_points(Point3 p0, Point3 p1) { auto s = std::make_shared<Shape>(); s->kind = Shape::CuboidK; s->center = p0; s->a = p1; return s; }
+};
+// shape/src/simple.rs:33-66 (new_anyspin's make_coord_system is the library's business: pass the radial)
+struct Disk {
+    Point3 center;
+    Vec3 normal, radial;
+    static Disk create(Point3 center, Vec3 normal, Vec3 radial) { return {center, normal, radial}; }
+    operator ShapeRef() const { auto s = std::make_shared<Shape>(); s->kind = Shape::DiskK; s->center = center; s->a = normal; s->b = radial; return s; }
+};
+// IsoBlas::<Sphere>::build, shape/src/blas.rs:60-69
+struct IsoBlas {
+    struct Ball { Point3 center; float radius; };
+    static ShapeRef build(const std::vector<Ball> &balls) {
+        auto s = std::make_shared<Shape>();
+        s->kind = Shape::SphereBlasK;
+        for (const Ball &b : balls) { s->P.push_back(b.center.x); s->P.push_back(b.center.y); s->P.push_back(b.center.z); s->P.push_back(b.radius); }
         return s;
     }
 };
@@ -298,12 +359,14 @@ struct DeltaLight {
         DeltaLight l; l.is_point = false; l.world_radius = world_radius; l.casting_dir = casting_dir; l.color = radiance; return l;
     }
 };
-struct SamplableShape {
-    bool is_sphere = true;
+struct SamplableShape {  // light/src/sample_shape.rs:38-43
+    enum Kind { SphereK, TriangleK, QuadK, DiskK } kind = SphereK;
     Point3 p0, p1, p2;
     float radius = 0.0f;
     static SamplableShape Sphere(Point3 center, float radius) { SamplableShape s; s.p0 = center; s.radius = radius; return s; }
-    static SamplableShape Triangle(Point3 p0, Point3 p1, Point3 p2) { SamplableShape s; s.is_sphere = false; s.p0 = p0; s.p1 = p1; s.p2 = p2; return s; }
+    static SamplableShape Triangle(Point3 p0, Point3 p1, Point3 p2) { SamplableShape s; s.kind = TriangleK; s.p0 = p0; s.p1 = p1; s.p2 = p2; return s; }
+    static SamplableShape Quad(const shape::ParallelQuad &q) { SamplableShape s; s.kind = QuadK; s.p0 = q.origin; s.p1 = q.side_u; s.p2 = q.side_v; return s; }
+    static SamplableShape Disk(const shape::Disk &d) { SamplableShape s; s.kind = DiskK; s.p0 = d.center; s.p1 = d.normal; s.p2 = d.radial; return s; }
 };
 struct DiffuseAreaLight {
     Color emit_radiance;
@@ -368,8 +431,15 @@ public:
                 auto si = shape_ids.find(in.shape.get());
                 if (si == shape_ids.end()) {
                     const Shape &sh = *in.shape;
-                    int id = sh.is_sphere ? check(pbrs_scene_add_sphere(s, sh.center.data(), sh.radius), "add_sphere")
-                                          : check(pbrs_scene_add_mesh(s, sh.P.data(), sh.N.data(), sh.UV.data(), uint32_t(sh.P.size() / 3), sh.idx.data(), uint32_t(sh.idx.size() / 3)), "add_mesh");
+                    int id = -1;
+                    switch (sh.kind) {
+                    case Shape::SphereK: id = check(pbrs_scene_add_sphere(s, sh.center.data(), sh.radius), "add_sphere"); break;
+                    case Shape::MeshK: id = check(pbrs_scene_add_mesh(s, sh.P.data(), sh.N.data(), sh.UV.data(), uint32_t(sh.P.size() / 3), sh.idx.data(), uint32_t(sh.idx.size() / 3)), "add_mesh"); break;
+                    case Shape::QuadK: id = check(pbrs_scene_add_quad(s, sh.center.data(), sh.a.data(), sh.b.data()), "add_quad"); break;
+                    case Shape::CuboidK: id = check(pbrs_scene_add_cuboid(s, sh.center.data(), sh.a.data()), "add_cuboid"); break;
+                    case Shape::DiskK: id = check(pbrs_scene_add_disk(s, sh.center.data(), sh.a.data(), sh.b.data()), "add_disk"); break;
+                    case Shape::SphereBlasK: id = check(pbrs_scene_add_sphere_blas(s, sh.P.data(), uint32_t(sh.P.size() / 4)), "add_sphere_blas"); break;
+                    }
                     si = shape_ids.emplace(in.shape.get(), id).first;
                 }
                 if (in.has_transform) check(pbrs_scene_add_instance(s, si->second, mi->second, &in.transform.fwd[0][0], &in.transform.inv[0][0]), "add_instance");
@@ -380,8 +450,13 @@ public:
                 else check(pbrs_scene_add_distant_light(s, l.casting_dir.data(), l.color.data(), l.world_radius), "add_distant_light");
             }
             for (const light::DiffuseAreaLight &l : area_) {
-                if (l.shape.is_sphere) check(pbrs_scene_add_area_light_sphere(s, l.shape.p0.data(), l.shape.radius, l.emit_radiance.data()), "add_area_light_sphere");
-                else check(pbrs_scene_add_area_light_triangle(s, l.shape.p0.data(), l.shape.p1.data(), l.shape.p2.data(), l.emit_radiance.data()), "add_area_light_triangle");
+                const light::SamplableShape &q = l.shape;
+                switch (q.kind) {
+                case light::SamplableShape::SphereK: check(pbrs_scene_add_area_light_sphere(s, q.p0.data(), q.radius, l.emit_radiance.data()), "add_area_light_sphere"); break;
+                case light::SamplableShape::TriangleK: check(pbrs_scene_add_area_light_triangle(s, q.p0.data(), q.p1.data(), q.p2.data(), l.emit_radiance.data()), "add_area_light_triangle"); break;
+                case light::SamplableShape::QuadK: check(pbrs_scene_add_area_light_quad(s, q.p0.data(), q.p1.data(), q.p2.data(), l.emit_radiance.data()), "add_area_light_quad"); break;
+                case light::SamplableShape::DiskK: check(pbrs_scene_add_area_light_disk(s, q.p0.data(), q.p1.data(), q.p2.data(), l.emit_radiance.data()), "add_area_light_disk"); break;
+                }
             }
             if (env_kind_ == 0) check(pbrs_scene_set_env_constant(s, env_color_.data()), "set_env_constant");
             else if (env_kind_ == 1) check(pbrs_scene_set_env_fn(s, int(env_fn_)), "set_env_fn");

@@ -24,7 +24,13 @@ struct Hit {
 // ---------------- instance: tlas/src/instance.rs:47-72 ----------------
 static BBox shape_bbox(const Scene &sc, int shape_id) {
     const ShapeRef &s = sc.shapes[shape_id];
-    return s.kind == SHAPE_SPHERE ? sphere_bbox(sc.spheres[s.index]) : mesh_bbox(*sc.meshes[s.index]);
+    switch (s.kind) {
+    case SHAPE_SPHERE: return sphere_bbox(sc.spheres[s.index]);
+    case SHAPE_QUAD: return quad_bbox(sc.quads[s.index]);
+    case SHAPE_CUBOID: return cuboid_bbox(sc.cuboids[s.index]);
+    case SHAPE_DISK: return disk_bbox(sc.disks[s.index]);
+    default: return mesh_bbox(*sc.meshes[s.index]);
+    }
 }
 static BBox instance_bbox(const Scene &sc, const Instance &in) {
     return affine_bbox(in.xf.fwd, shape_bbox(sc, in.shape_id));
@@ -39,6 +45,12 @@ static bool instance_intersect(const Scene &sc, const Instance &in, const Ray &r
     if (s.kind == SHAPE_SPHERE) {
         if (g_diag) g_diag->n_spheres++;
         if (!sphere_intersect(sc.spheres[s.index], inv_ray, &hit)) return false;
+    } else if (s.kind == SHAPE_QUAD) {
+        if (!quad_intersect(sc.quads[s.index], inv_ray, &hit)) return false;
+    } else if (s.kind == SHAPE_CUBOID) {
+        if (!cuboid_intersect(sc.cuboids[s.index], inv_ray, &hit)) return false;
+    } else if (s.kind == SHAPE_DISK) {
+        if (!disk_intersect(sc.disks[s.index], inv_ray, &hit)) return false;
     } else {
         if (!mesh_intersect(*sc.meshes[s.index], inv_ray, &hit, &prim)) return false;
     }
@@ -56,6 +68,9 @@ static bool instance_occludes(const Scene &sc, const Instance &in, const Ray &ra
         if (g_diag) g_diag->n_spheres++;
         return sphere_occludes(sc.spheres[s.index], inv_ray);
     }
+    if (s.kind == SHAPE_QUAD) return quad_occludes(sc.quads[s.index], inv_ray);
+    if (s.kind == SHAPE_CUBOID) return cuboid_occludes(sc.cuboids[s.index], inv_ray);
+    if (s.kind == SHAPE_DISK) return disk_occludes(sc.disks[s.index], inv_ray);
     return mesh_occludes(*sc.meshes[s.index], inv_ray);
 }
 
@@ -625,6 +640,44 @@ int oracle_scene_add_mesh(oracle_scene *s, const float *P, const float *N, const
     s->sc.shapes.push_back(ShapeRef{SHAPE_MESH, (int)s->sc.meshes.size() - 1});
     return (int)s->sc.shapes.size() - 1;
 }
+int oracle_scene_add_quad(oracle_scene *s, const float o[3], const float su[3], const float sv[3]) {
+    s->sc.quads.push_back(Quad{V3{o[0], o[1], o[2]}, V3{su[0], su[1], su[2]}, V3{sv[0], sv[1], sv[2]}});
+    s->sc.shapes.push_back(ShapeRef{SHAPE_QUAD, (int)s->sc.quads.size() - 1});
+    return (int)s->sc.shapes.size() - 1;
+}
+int oracle_scene_add_cuboid(oracle_scene *s, const float p0[3], const float p1[3]) {
+    s->sc.cuboids.push_back(cuboid_from_points(V3{p0[0], p0[1], p0[2]}, V3{p1[0], p1[1], p1[2]}));
+    s->sc.shapes.push_back(ShapeRef{SHAPE_CUBOID, (int)s->sc.cuboids.size() - 1});
+    return (int)s->sc.shapes.size() - 1;
+}
+// Disk::new, simple.rs:42-52: the normal is normalised; the two asserts are argument errors here
+static int make_disk(const float c[3], const float n[3], const float rad[3], Disk *out) {
+    V3 nv{n[0], n[1], n[2]};
+    float n2 = norm_squared(nv);
+    if (!(n2 != 0.0f && std::isfinite(n2))) return fail(PBRS_ERR_INVALID_ARG, "disk: normal cannot be normalised");
+    V3 normal = hat(nv), radial{rad[0], rad[1], rad[2]};
+    if (!std::isfinite(norm_squared(radial))) return fail(PBRS_ERR_INVALID_ARG, "disk: radial is not finite");
+    if (!(std::fabs(dot(radial, normal)) < 1e-6f)) return fail(PBRS_ERR_INVALID_ARG, "disk: radial is not perpendicular to the normal");
+    *out = Disk{V3{c[0], c[1], c[2]}, normal, radial};
+    return 0;
+}
+int oracle_scene_add_disk(oracle_scene *s, const float c[3], const float n[3], const float rad[3]) {
+    Disk d;
+    if (int rc = make_disk(c, n, rad, &d)) return rc;
+    s->sc.disks.push_back(d);
+    s->sc.shapes.push_back(ShapeRef{SHAPE_DISK, (int)s->sc.disks.size() - 1});
+    return (int)s->sc.shapes.size() - 1;
+}
+int oracle_scene_add_sphere_blas(oracle_scene *s, const float *centers_radii, uint32_t n) {
+    if (!centers_radii || n == 0) return fail(PBRS_ERR_INVALID_ARG, "sphere_blas: bad args");
+    for (uint32_t i = 0; i < 4 * n; ++i)
+        if (std::isnan(centers_radii[i])) return fail(PBRS_ERR_INVALID_ARG, "sphere_blas: NaN (Sphere::from_raw asserts)");
+    auto m = std::make_unique<Mesh>();
+    sphere_blas_build(*m, centers_radii, n);
+    s->sc.meshes.push_back(std::move(m));
+    s->sc.shapes.push_back(ShapeRef{SHAPE_MESH, (int)s->sc.meshes.size() - 1});
+    return (int)s->sc.shapes.size() - 1;
+}
 int oracle_scene_add_instance(oracle_scene *s, int shape, int mtl, const float *fwd, const float *inv) {
     if (shape < 0 || shape >= (int)s->sc.shapes.size() || mtl < 0 || mtl >= (int)s->sc.materials.size())
         return fail(PBRS_ERR_INVALID_ARG, "instance: bad ids");
@@ -664,6 +717,24 @@ int oracle_scene_add_area_light_triangle(oracle_scene *s, const float p0[3], con
     l.tri = IsoTriangle{V3{p0[0], p0[1], p0[2]}, V3{p1[0], p1[1], p1[2]}, V3{p2[0], p2[1], p2[2]}};
     l.emit = rgb(e[0], e[1], e[2]);
     l.area = isotri_area(l.tri);
+    s->sc.area_lights.push_back(l);
+    return 0;
+}
+int oracle_scene_add_area_light_quad(oracle_scene *s, const float o[3], const float su[3], const float sv[3], const float e[3]) {
+    AreaLight l{};
+    l.shape_kind = AREA_QUAD;
+    l.quad = Quad{V3{o[0], o[1], o[2]}, V3{su[0], su[1], su[2]}, V3{sv[0], sv[1], sv[2]}};
+    l.emit = rgb(e[0], e[1], e[2]);
+    l.area = quad_area(l.quad);
+    s->sc.area_lights.push_back(l);
+    return 0;
+}
+int oracle_scene_add_area_light_disk(oracle_scene *s, const float c[3], const float n[3], const float rad[3], const float e[3]) {
+    AreaLight l{};
+    l.shape_kind = AREA_DISK;
+    if (int rc = make_disk(c, n, rad, &l.disk)) return rc;
+    l.emit = rgb(e[0], e[1], e[2]);
+    l.area = disk_area(l.disk);
     s->sc.area_lights.push_back(l);
     return 0;
 }

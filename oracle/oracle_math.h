@@ -47,7 +47,7 @@ inline void panic_flag(int kind) {
 enum {
     P_SPHERE_INSIDE = 0, P_TBN = 1, P_HAT = 2, P_BSDF_FRAME = 3, P_MESH_UV = 4,
     P_EMPTY_BXDFS = 5, P_LOG_SAMPLE = 6, P_FRESNEL = 7, P_LAMBERT_WO = 8, P_PERLIN = 9,
-    P_REFRACT = 10, P_MISC = 11
+    P_REFRACT = 10, P_MISC = 11, P_STACK = 12 /* GPU side only */, P_QUAD = 13
 };
 
 // ---- Rust f32 method semantics ----
@@ -90,6 +90,7 @@ inline float sse_max(float a, float b) { return a > b ? a : b; }
 struct V3 {
     float x, y, z;
     float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+    float &operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
     float &at(int i) { return i == 0 ? x : (i == 1 ? y : z); }
 };
 inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }

@@ -114,6 +114,120 @@ inline bool isotri_intersect(const IsoTriangle &t, const Ray &r, Interaction *ou
     return true;
 }
 
+// ---------------- ParallelQuad: shape/src/simple.rs:69-164 ----------------
+struct Quad {
+    V3 origin, side_u, side_v;
+};
+inline BBox quad_bbox(const Quad &q) {  // :105-113
+    BBox bu = bbox_new(q.origin, q.origin + q.side_u);
+    BBox bv = bbox_new(q.origin + q.side_v, q.origin + q.side_u + q.side_v);
+    return bbox_union(bu, bv);
+}
+// :136-137 (Q11: u and v come from cross-product NORMS, so the mirrored extensions pass too)
+inline void quad_uv(const Quad &q, V3 coarse_hit, float *u, float *v) {
+    V3 a = q.side_u, b = q.side_v, d = coarse_hit - q.origin;
+    *v = norm(cross(a, d)) / norm(cross(a, b));
+    *u = norm(cross(b, d)) / norm(cross(b, a));
+}
+inline bool inside01(float x) { return 0.0f <= x && x <= 1.0f; }  // math/src/float.rs:210-213
+// :120-150.  The accurate-vs-coarse assert (:140-147) is counted as P_QUAD and the hit kept.
+inline bool quad_intersect(const Quad &q, const Ray &r, Interaction *out) {
+    V3 normal = facing(cross(q.side_u, q.side_v), r.dir);
+    float t = dot(q.origin - r.origin, normal) / dot(r.dir, normal);
+    if (!truncated_t(r, t)) return false;
+    V3 coarse_hit = position_at(r, t);
+    float u, v;
+    quad_uv(q, coarse_hit, &u, &v);
+    if (!(inside01(v) && inside01(u))) return false;
+    V3 accurate_hit = q.origin + u * q.side_u + q.side_v * v;
+    if (!(distance_to(accurate_hit, coarse_hit) < 1e-3f)) panic_flag(P_QUAD);
+    *out = with_dpdu(isect_new(accurate_hit, t, u, v, hat(normal), -r.dir), q.side_u);
+    return true;
+}
+// :151-163 (Q11: `t` is the reciprocal of the plane distance)
+inline bool quad_occludes(const Quad &q, const Ray &r) {
+    V3 normal = cross(q.side_u, q.side_v);
+    float t = dot(r.dir, normal) / dot(q.origin - r.origin, normal);
+    if (!truncated_t(r, t)) return false;
+    float u, v;
+    quad_uv(q, position_at(r, t), &u, &v);
+    return inside01(v) && inside01(u);
+}
+
+// ---------------- Cuboid: shape/src/simple.rs:166-182,335-416 ----------------
+struct Cuboid {
+    V3 mn, mx;
+};
+inline Cuboid cuboid_from_points(V3 p0, V3 p1) {  // :173-181 with float::min_max (float.rs:197-203)
+    Cuboid c;
+    for (int k = 0; k < 3; ++k) {
+        if (p0[k] < p1[k]) { c.mn[k] = p0[k]; c.mx[k] = p1[k]; } else { c.mn[k] = p1[k]; c.mx[k] = p0[k]; }
+    }
+    return c;
+}
+inline BBox cuboid_bbox(const Cuboid &c) { return bbox_new(c.mn, c.mx); }
+// :343-411
+inline bool cuboid_intersect(const Cuboid &c, const Ray &r, Interaction *out) {
+    struct HitInfo { float t, bound; int axis; };
+    HitInfo hit_min{0.0f, kInf, 0}, hit_max{r.t_max, -kInf, 0};
+    for (int axis = 0; axis < 3; ++axis) {
+        float inv_dir = 1.0f / r.dir[axis];
+        float t0 = (c.mn[axis] - r.origin[axis]) * inv_dir;
+        float t1 = (c.mx[axis] - r.origin[axis]) * inv_dir;
+        HitInfo hit_0{t0, c.mn[axis], axis}, hit_1{t1, c.mx[axis], axis};
+        if (t0 > t1) { std::swap(hit_0, hit_1); std::swap(t0, t1); }
+        if (t0 > hit_min.t) hit_min = hit_0;
+        if (t1 < hit_max.t) hit_max = hit_1;
+        if (hit_max.t < hit_min.t) return false;
+    }
+    if (std::isnan(hit_min.t) || std::isnan(hit_max.t)) panic_flag(P_MISC);  // Interval::new, float.rs:162-164
+    float lo = hit_min.t < hit_max.t ? hit_min.t : hit_max.t, hi = hit_min.t < hit_max.t ? hit_max.t : hit_min.t;
+    HitInfo h = (0.0f >= lo && 0.0f <= hi) ? hit_max : hit_min;  // Interval::contains(0.0)
+    if (std::isinf(h.bound)) return false;
+    V3 hit_pos = position_at(r, h.t);
+    hit_pos[h.axis] = h.bound;
+    V3 normal{0, 0, 0}, tangent{0, 0, 0};
+    normal[h.axis] = f_signum(r.dir[h.axis]) * -1.0f;
+    tangent[(h.axis + 1) % 3] = 1.0f;
+    *out = with_dpdu(isect_new(hit_pos, h.t, 0.5f, 0.5f, normal, -r.dir), tangent);
+    return true;
+}
+inline bool cuboid_occludes(const Cuboid &c, const Ray &r) { return bbox_intersect(cuboid_bbox(c), r); }  // :412-415
+
+// ---------------- Disk: shape/src/simple.rs:33-66,291-333 ----------------
+struct Disk {
+    V3 center, normal, radial;  // normal is unit length (Disk::new, :42-51)
+};
+inline BBox disk_bbox(const Disk &d) {  // :298-305
+    V3 v1, v2;
+    make_coord_system(d.normal, &v1, &v2);
+    v1 = v1 * norm(d.radial);
+    v2 = v2 * norm(d.radial);
+    return bbox_union(bbox_new(d.center + v1 + v2, d.center + v1 - v2), bbox_new(d.center - v1 - v2, d.center - v1 + v2));
+}
+// :306-326
+inline bool disk_intersect(const Disk &d, const Ray &r, Interaction *out) {
+    float t = dot(d.center - r.origin, d.normal) / dot(r.dir, d.normal);
+    if (!truncated_t(r, t)) return false;
+    V3 isect_point = position_at(r, t);
+    if (!(squared_distance_to(isect_point, d.center) <= norm_squared(d.radial))) return false;
+    V3 cp = isect_point - d.center;
+    cp = cp - dot(cp, d.normal) * d.normal;
+    if (!(std::fabs(dot(cp, d.normal)) < 1e-6f)) panic_flag(P_MISC);
+    V3 normal = d.normal * f_signum(dot(d.normal, -r.dir));
+    V3 tangent = hat(cross(normal, cp));
+    float u = std::atan2(dot(cross(d.radial, cp), normal), dot(d.radial, cp));
+    u = f_fract(u * kFrac1Pi + 1.0f);
+    float v = norm(cp) / norm(d.radial);
+    *out = with_dpdu(isect_new(d.center + cp, t, u, v, normal, -r.dir), tangent);
+    return true;
+}
+// :328-332 (Q10: the ray extent is not consulted at all)
+inline bool disk_occludes(const Disk &d, const Ray &r) {
+    float t = dot(d.center - r.origin, d.normal) / dot(r.dir, d.normal);
+    return squared_distance_to(position_at(r, t), d.center) <= norm_squared(d.radial);
+}
+
 // ---------------- BLAS: shape/src/blas.rs ----------------
 struct BlasNode {
     BBox bbox;
@@ -131,6 +245,7 @@ struct Mesh {
     std::vector<V3> positions, normals;
     std::vector<float> us, vs;
     std::vector<MeshTri> tris;  // permuted in place by the build (blas.rs:388)
+    std::vector<Sphere> balls;  // IsoBlas<Sphere> (blas.rs:36-70): primitives are these, `tris` only carries box + index
     std::unique_ptr<BlasNode> root;
 };
 
@@ -224,6 +339,17 @@ inline void mesh_build(Mesh &m, const float *P, const float *N, const float *UV,
     m.root = blas_build(m.tris, 0, ntris);
 }
 
+// IsoBlas::build, blas.rs:60-69
+inline void sphere_blas_build(Mesh &m, const float *centers_radii, uint32_t n) {
+    m.balls.resize(n);
+    m.tris.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        m.balls[i] = Sphere{V3{centers_radii[4 * i], centers_radii[4 * i + 1], centers_radii[4 * i + 2]}, centers_radii[4 * i + 3]};
+        m.tris[i] = MeshTri{0, 0, 0, sphere_bbox(m.balls[i]), i};
+    }
+    m.root = blas_build(m.tris, 0, n);
+}
+
 // blas.rs:161-207 (note the (i, k, j) destructuring: p1 = pos[idx.2], p2 = pos[idx.1])
 inline bool mesh_intersect_triangle(const Mesh &m, const MeshTri &tri, const Ray &r, Interaction *out) {
     uint32_t i = tri.i0, k = tri.i1, j = tri.i2;
@@ -273,9 +399,16 @@ inline bool mesh_intersect(const Mesh &m, const Ray &r, Interaction *out, uint32
         if (!bbox_intersect(node->bbox, ray)) continue;
         if (node->is_leaf) {
             for (uint32_t s = node->begin; s < node->end; ++s) {
-                if (g_diag) g_diag->n_tris++;
                 Interaction h;
-                if (mesh_intersect_triangle(m, m.tris[s], ray, &h)) {
+                bool got;
+                if (!m.balls.empty()) {  // blas.rs:267-270: the closure is the shape's own intersect
+                    if (g_diag) g_diag->n_spheres++;
+                    got = sphere_intersect(m.balls[m.tris[s].orig], ray, &h);
+                } else {
+                    if (g_diag) g_diag->n_tris++;
+                    got = mesh_intersect_triangle(m, m.tris[s], ray, &h);
+                }
+                if (got) {
                     if (h.ray_t < outer.ray_t) { outer = h; best_prim = m.tris[s].orig; }
                 }
             }
@@ -299,6 +432,11 @@ inline bool blas_pred(const Mesh &m, const BlasNode *n, const Ray &r) {
     if (!bbox_intersect(n->bbox, r)) return false;
     if (n->is_leaf) {
         for (uint32_t s = n->begin; s < n->end; ++s) {
+            if (!m.balls.empty()) {
+                if (g_diag) g_diag->n_spheres++;
+                if (sphere_occludes(m.balls[m.tris[s].orig], r)) return true;
+                continue;
+            }
             if (g_diag) g_diag->n_tris++;
             if (mesh_intersect_triangle_pred(m, m.tris[s], r)) return true;
         }
@@ -402,11 +540,13 @@ struct DeltaLight {
     float world_radius;
     V3 casting_dir;
 };
-enum AreaShapeKind { AREA_SPHERE = 0, AREA_TRIANGLE = 1 };
+enum AreaShapeKind { AREA_SPHERE = 0, AREA_TRIANGLE = 1, AREA_QUAD = 2, AREA_DISK = 3 };
 struct AreaLight {
     int shape_kind;
     Sphere sphere;
     IsoTriangle tri;
+    Quad quad;
+    Disk disk;
     Color emit;
     float area;
 };
@@ -459,24 +599,55 @@ inline Interaction isotri_sample(const IsoTriangle &t, float u, float v) {
 }
 inline float isotri_area(const IsoTriangle &t) { return norm(cross(t.p0 - t.p1, t.p2 - t.p1)) * 0.5f; }
 
+// sample_shape.rs:296-309 (the normal is the unnormalised cross product)
+inline Interaction quad_sample(const Quad &q, float u, float v) {
+    V3 position = q.origin + u * q.side_u + v * q.side_v;
+    return isect_rayless(position, u, v, cross(q.side_u, q.side_v));
+}
+inline float quad_area(const Quad &q) { return norm(cross(q.side_u, q.side_v)); }
+// sample_shape.rs:257-274
+inline Interaction disk_sample(const Disk &d, float u, float v) {
+    float cos_t, sin_t;
+    concentric_sample_disk(u, v, &cos_t, &sin_t);
+    V3 radial2 = cross(d.normal, d.radial);
+    V3 cp = d.radial * cos_t + radial2 * sin_t;
+    return isect_rayless(d.center + cp, u, v, d.normal);
+}
+inline Interaction disk_sample_towards(const Disk &d, const Interaction &target, float u, float v) {
+    Interaction res = disk_sample(d, u, v);
+    res.normal = facing(res.normal, target.normal);
+    return res;
+}
+inline float disk_area(const Disk &d) { return norm_squared(d.radial) * kPi; }
+
 inline bool area_shape_intersect(const AreaLight &l, const Ray &r, Interaction *out) {
-    return l.shape_kind == AREA_SPHERE ? sphere_intersect(l.sphere, r, out) : isotri_intersect(l.tri, r, out);
+    switch (l.shape_kind) {
+    case AREA_SPHERE: return sphere_intersect(l.sphere, r, out);
+    case AREA_TRIANGLE: return isotri_intersect(l.tri, r, out);
+    case AREA_QUAD: return quad_intersect(l.quad, r, out);
+    default: return disk_intersect(l.disk, r, out);
+    }
 }
 // sample_shape.rs:28-33 default pdf_at (Q12: distance, not distance squared)
 inline bool area_shape_pdf_at(const AreaLight &l, const Interaction &ref, V3 wi, float *pdf) {
     if (l.shape_kind == AREA_SPHERE) return sphere_pdf_at(l.sphere, ref, wi, pdf);
     Ray ray = spawn_ray(ref, wi);
     Interaction hit;
-    if (!isotri_intersect(l.tri, ray, &hit)) return false;
+    if (!area_shape_intersect(l, ray, &hit)) return false;
     *pdf = distance_to(ref.pos, hit.pos) / (std::fabs(dot(hit.normal, -wi)) * l.area);
     return true;
 }
 inline Interaction area_shape_sample_towards(const AreaLight &l, const Interaction &t, float u, float v) {
-    return l.shape_kind == AREA_SPHERE ? sphere_sample_towards(l.sphere, t, u, v) : isotri_sample(l.tri, u, v);
+    switch (l.shape_kind) {
+    case AREA_SPHERE: return sphere_sample_towards(l.sphere, t, u, v);
+    case AREA_TRIANGLE: return isotri_sample(l.tri, u, v);
+    case AREA_QUAD: return quad_sample(l.quad, u, v);
+    default: return disk_sample_towards(l.disk, t, u, v);
+    }
 }
 
 // ---------------- instances + TLAS: tlas/src/instance.rs, tlas/src/bvh.rs ----------------
-enum ShapeKind { SHAPE_SPHERE = 0, SHAPE_MESH = 1 };
+enum ShapeKind { SHAPE_SPHERE = 0, SHAPE_MESH = 1, SHAPE_QUAD = 2, SHAPE_CUBOID = 3, SHAPE_DISK = 4 };  // a sphere BLAS is a SHAPE_MESH
 struct ShapeRef {
     int kind;
     int index;  // into spheres / meshes
@@ -502,6 +673,9 @@ struct Scene {
     std::vector<Material> materials;
     std::vector<ShapeRef> shapes;
     std::vector<Sphere> spheres;
+    std::vector<Quad> quads;
+    std::vector<Cuboid> cuboids;
+    std::vector<Disk> disks;
     std::vector<std::unique_ptr<Mesh>> meshes;
     std::vector<Instance> instances;
     std::vector<DeltaLight> delta_lights;

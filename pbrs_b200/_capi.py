@@ -24,7 +24,7 @@ ERR_INVALID_ARG, ERR_STATE, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_OOM = 
 
 PANIC_NAMES = [
     "sphere_inside", "tbn", "hat", "bsdf_frame", "mesh_uv", "empty_bxdfs", "log_sample",
-    "fresnel", "lambert_wo", "perlin", "refract", "misc", "r12", "r13", "r14", "r15",
+    "fresnel", "lambert_wo", "perlin", "refract", "misc", "stack", "quad", "r14", "r15",
 ]
 
 
@@ -110,11 +110,17 @@ SCENE_API = {
     "scene_add_material": (C.c_int, [P, C.POINTER(MaterialDesc)]),
     "scene_add_sphere": (C.c_int, [P, f3, C.c_float]),
     "scene_add_mesh": (C.c_int, [P, f3, f3, f3, C.c_uint32, c_u32_p, C.c_uint32]),
+    "scene_add_quad": (C.c_int, [P, f3, f3, f3]),
+    "scene_add_cuboid": (C.c_int, [P, f3, f3]),
+    "scene_add_disk": (C.c_int, [P, f3, f3, f3]),
+    "scene_add_sphere_blas": (C.c_int, [P, f3, C.c_uint32]),
     "scene_add_instance": (C.c_int, [P, C.c_int, C.c_int, f3, f3]),
     "scene_add_point_light": (C.c_int, [P, f3, f3]),
     "scene_add_distant_light": (C.c_int, [P, f3, f3, C.c_float]),
     "scene_add_area_light_sphere": (C.c_int, [P, f3, C.c_float, f3]),
     "scene_add_area_light_triangle": (C.c_int, [P, f3, f3, f3, f3]),
+    "scene_add_area_light_quad": (C.c_int, [P, f3, f3, f3, f3]),
+    "scene_add_area_light_disk": (C.c_int, [P, f3, f3, f3, f3]),
     "scene_set_env_constant": (C.c_int, [P, f3]),
     "scene_set_env_fn": (C.c_int, [P, C.c_int]),
     "scene_set_env_image": (C.c_int, [P, C.c_uint32, C.c_uint32, c_u8_p, f3]),

@@ -144,6 +144,36 @@ int pbrs_scene_add_mesh(pbrs_scene *s, const float *P, const float *N, const flo
     NEED(nverts > 0 && ntris > 0, "add_mesh: empty mesh");
     return host_add_mesh(s->impl, P, N, UV, nverts, idx, ntris);
 }
+int pbrs_scene_add_quad(pbrs_scene *s, const float origin[3], const float side_u[3], const float side_v[3]) {
+    NEED(s && origin && side_u && side_v, "add_quad: null argument");
+    NOT_COMMITTED(s);
+    NEED(finite3(origin) && finite3(side_u) && finite3(side_v), "add_quad: non-finite argument");
+    return host_add_simple(s->impl, PBRS_SHAPE_QUAD, origin, side_u, side_v);
+}
+int pbrs_scene_add_cuboid(pbrs_scene *s, const float p0[3], const float p1[3]) {
+    NEED(s && p0 && p1, "add_cuboid: null argument");
+    NOT_COMMITTED(s);
+    NEED(finite3(p0) && finite3(p1), "add_cuboid: non-finite argument");
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {  // float::min_max, math/src/float.rs:197-203
+        if (p0[k] < p1[k]) { mn[k] = p0[k]; mx[k] = p1[k]; } else { mn[k] = p1[k]; mx[k] = p0[k]; }
+    }
+    return host_add_simple(s->impl, PBRS_SHAPE_CUBOID, mn, mx, nullptr);
+}
+int pbrs_scene_add_disk(pbrs_scene *s, const float center[3], const float normal[3], const float radial[3]) {
+    NEED(s && center && normal && radial, "add_disk: null argument");
+    NOT_COMMITTED(s);
+    NEED(finite3(center), "add_disk: non-finite centre");
+    float n[3];
+    if (int rc = host_make_disk(center, normal, radial, n)) return rc;
+    return host_add_simple(s->impl, PBRS_SHAPE_DISK, center, n, radial);
+}
+int pbrs_scene_add_sphere_blas(pbrs_scene *s, const float *centers_radii, uint32_t n) {
+    NEED(s && centers_radii, "add_sphere_blas: null argument");
+    NOT_COMMITTED(s);
+    NEED(n > 0, "add_sphere_blas: no spheres");
+    return host_add_sphere_blas(s->impl, centers_radii, n);
+}
 int pbrs_scene_add_instance(pbrs_scene *s, int shape_id, int material_id, const float fwd4x4[16], const float inv4x4[16]) {
     NEED(s, "add_instance: null scene");
     NOT_COMMITTED(s);
@@ -197,6 +227,34 @@ int pbrs_scene_add_area_light_triangle(pbrs_scene *s, const float p0[3], const f
     float a[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]}, b[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
     float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
     l.area = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) * 0.5f;
+    s->impl.area_lights.push_back(l);
+    return 0;
+}
+int pbrs_scene_add_area_light_quad(pbrs_scene *s, const float origin[3], const float side_u[3], const float side_v[3], const float emit[3]) {
+    NEED(s && origin && side_u && side_v && emit, "add_area_light_quad: null argument");
+    NOT_COMMITTED(s);
+    AreaLightRec l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = PBRS_AREA_QUAD;
+    for (int k = 0; k < 3; ++k) { l.p0[k] = origin[k]; l.p1[k] = side_u[k]; l.p2[k] = side_v[k]; l.emit[k] = emit[k]; }
+    // ParallelQuad::area, light/src/sample_shape.rs:306-308: |side_u x side_v|
+    const float *a = side_u, *b = side_v;
+    float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    l.area = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    s->impl.area_lights.push_back(l);
+    return 0;
+}
+int pbrs_scene_add_area_light_disk(pbrs_scene *s, const float center[3], const float normal[3], const float radial[3], const float emit[3]) {
+    NEED(s && center && normal && radial && emit, "add_area_light_disk: null argument");
+    NOT_COMMITTED(s);
+    AreaLightRec l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = PBRS_AREA_DISK;
+    float n[3];
+    if (int rc = host_make_disk(center, normal, radial, n)) return rc;
+    for (int k = 0; k < 3; ++k) { l.p0[k] = center[k]; l.p1[k] = n[k]; l.p2[k] = radial[k]; l.emit[k] = emit[k]; }
+    // Disk::area, light/src/sample_shape.rs:271-273: |radial|^2 * PI
+    l.area = (radial[0] * radial[0] + radial[1] * radial[1] + radial[2] * radial[2]) * kPi;
     s->impl.area_lights.push_back(l);
     return 0;
 }

@@ -213,6 +213,11 @@ PB_DEV bool sphere_occludes(vec3 c, float radius, const Ray &r) {
     if (!sphere_roots(c, radius, r, t0, t1)) return false;
     return in_extent(t0, r.t_max) && in_extent(t1, r.t_max);
 }
+// One sphere of a sphere BLAS, out of line so the triangle-run loop only carries a call site.
+PB_CALL bool ball_test(vec3 c, float radius, const Ray &r, bool any, float &t) {
+    if (any) return sphere_occludes(c, radius, r);
+    return sphere_hit_t(c, radius, r, t);
+}
 // The full Interaction of Sphere::intersect in the sphere's own space.  D1: a hit from
 // inside trips Interaction::new's assert upstream; flag it and face the normal to the ray.
 // need_uv = false skips the (u, v) of the hit (two FP64 transcendentals): only image textures read them.

@@ -31,6 +31,7 @@ namespace pbrs {
 
 constexpr float kEps = 1.1920929e-7f;  // f32::EPSILON
 constexpr float kPi = 3.14159265358979323846f;
+constexpr float kFrac1Pi = 0.318309886183790671537767526745028724f;  // std::f32::consts::FRAC_1_PI
 constexpr float kInvPi = 0.318309886183790671537767526745028724f;
 constexpr float kHalfPi = 1.57079632679489661923132169163975144f;
 #define PB_INF (__builtin_huge_valf())
@@ -97,7 +98,8 @@ PB_DEV void flag(Diag &d, int kind) { d.panics |= 1u << kind; }
 enum {
     P_SPHERE_INSIDE = 0, P_TBN = 1, P_HAT = 2, P_BSDF_FRAME = 3, P_MESH_UV = 4, P_EMPTY_BXDFS = 5,
     P_LOG_SAMPLE = 6, P_FRESNEL = 7, P_LAMBERT_WO = 8, P_PERLIN = 9, P_REFRACT = 10, P_MISC = 11,
-    P_STACK = 12  // a traversal stack overflowed (never with scenes pbrs_scene_commit accepts)
+    P_STACK = 12,  // a traversal stack overflowed (never with scenes pbrs_scene_commit accepts)
+    P_QUAD = 13    // ParallelQuad's accurate-vs-coarse hit assert, shape/src/simple.rs:140-147
 };
 
 // Vec3::hat, hcm.rs:112-117

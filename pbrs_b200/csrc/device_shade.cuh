@@ -7,6 +7,7 @@
 // call, and the integrators call it two or three times per bounce; here it is built once).
 #pragma once
 #include "device_geom.cuh"
+#include "device_simple.cuh"
 
 namespace pbrs {
 
@@ -642,23 +643,45 @@ PB_CALL bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, v
         pos = h.pos; normal = h.normal;
         return true;
     }
-    return isotri_intersect(l.p0, l.p1, l.p2, r, pos, normal, dg);
+    if (l.kind == PBRS_AREA_TRIANGLE) return isotri_intersect(l.p0, l.p1, l.p2, r, pos, normal, dg);
+    Isect h;
+    if (l.kind == PBRS_AREA_QUAD) {
+        if (!quad_intersect(l.p0, l.p1, l.p2, r, h, dg)) return false;
+    } else {
+        if (!disk_intersect(l.p0, l.p1, l.p2, r, h, dg)) return false;
+    }
+    pos = h.pos; normal = h.normal;
+    return true;
 }
 // sample_shape.rs:28-33 default pdf_at (Q12: distance, not distance squared); sphere override :238
 PB_CALL bool area_shape_pdf_at(const AreaLight &l, const Isect &ref, vec3 wi, float &pdf, Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) return sphere_pdf_at(l.p0, l.p1.x, ref.pos, wi, pdf);
     Ray ray = spawn_ray(ref, wi);
     vec3 pos, normal;
-    if (!isotri_intersect(l.p0, l.p1, l.p2, ray, pos, normal, dg)) return false;
+    if (!area_shape_intersect(l, ray, pos, normal, dg)) return false;
     pdf = len(ref.pos - pos) / (fabsf(dot(normal, -wi)) * l.area);
     return true;
 }
-// sample_shape.rs:197 (sphere), :275-293 (triangle)
+// sample_shape.rs:197 (sphere), :275-293 (triangle), :296-305 (quad), :257-269 (disk)
 PB_DEV void area_shape_sample_towards(const AreaLight &l, const Isect &target, float u, float v, vec3 &pos, vec3 &normal,
                                       Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) {
         sphere_sample_towards(l.p0, l.p1.x, target.pos, u, v, pos, normal, dg);
         (void)isect_rayless(pos, u, v, normal, dg);
+        return;
+    }
+    if (l.kind == PBRS_AREA_QUAD) {  // :296-305: the normal is the unnormalised cross product
+        pos = l.p0 + u * l.p1 + v * l.p2;
+        normal = cross(l.p1, l.p2);
+        return;
+    }
+    if (l.kind == PBRS_AREA_DISK) {  // :257-269
+        float cos_t, sin_t;
+        concentric_sample_disk(u, v, cos_t, sin_t);
+        vec3 radial2 = cross(l.p1, l.p2);
+        vec3 cp = l.p2 * cos_t + radial2 * sin_t;
+        pos = l.p0 + cp;
+        normal = facing(l.p1, target.normal);
         return;
     }
     if (u + v > 1.0f) { float nu = 1.0f - v, nv = 1.0f - u; u = nu; v = nv; }

@@ -199,13 +199,19 @@ PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32
     if (kind == PBRS_SHAPE_SPHERE) {
         f4 s = ld16(sc.spheres + index);
         sphere_intersect(mk(s.x, s.y, s.z), s.w, o, h, dg, f2u(tail.z) != 0u);
+    } else if (kind != PBRS_SHAPE_MESH) {
+        if (!simple_intersect(sc.simples + index, kind, o, h, dg)) flag(dg, P_MISC);
     } else {
         TriVerts tv = load_tri(sc.tris + tri);
-        MeshHit mh;
-        mh.pos = mk(0, 0, 0); mh.normal = mk(0, 0, 1); mh.dpdu = mk(1, 0, 0); mh.t = 0; mh.u = 0; mh.v = 0;
-        if (!mesh_tri_shade(sc, tri, tv, o, mh, dg)) flag(dg, P_MISC);
-        h = isect_new(mh.pos, mh.t, mh.u, mh.v, mh.normal, -o.d, dg);
-        with_dpdu(h, mh.dpdu, dg);
+        if (tv.flags & PBRS_TRI_SPHERE) {
+            sphere_intersect(tv.p0, tv.p1.x, o, h, dg, f2u(tail.z) != 0u);
+        } else {
+            MeshHit mh;
+            mh.pos = mk(0, 0, 0); mh.normal = mk(0, 0, 1); mh.dpdu = mk(1, 0, 0); mh.t = 0; mh.u = 0; mh.v = 0;
+            if (!mesh_tri_shade(sc, tri, tv, o, mh, dg)) flag(dg, P_MISC);
+            h = isect_new(mh.pos, mh.t, mh.u, mh.v, mh.normal, -o.d, dg);
+            with_dpdu(h, mh.dpdu, dg);
+        }
     }
     const char *tb = reinterpret_cast<const char *>(sc.inst_trav + inst);
     f4 i0 = ld16(tb), i1 = ld16(tb + 16), i2 = ld16(tb + 32);

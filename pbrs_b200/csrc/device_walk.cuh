@@ -18,6 +18,7 @@
 // pass/fail outcome of every box is bit-identical to the reference's.
 #pragma once
 #include "device_geom.cuh"
+#include "device_simple.cuh"
 
 namespace pbrs {
 
@@ -115,7 +116,9 @@ PB_DEV int retest(float tl, float t_max) {
     return -1;
 }
 
-template <bool ANY, bool COUNT>
+// EXT = the scene holds quads / cuboids / disks or a sphere BLAS (DeviceScene::has_ext); without
+// them the leaf code is the sphere + triangle-mesh code alone (3.5 % faster on the C4 workload).
+template <bool ANY, bool COUNT, bool EXT = true>
 struct Walk {
     // ray in the current space (world on the TLAS level, object inside a mesh instance)
     vec3 o, d, rd;
@@ -257,10 +260,19 @@ struct Walk {
             uint32_t s = tri_base + first;
             while (true) {
                 TriVerts tv = load_tri(sc.tris + s);
-                if (COUNT) tc.tris++;
-                if (ANY) {
+                if (EXT && (tv.flags & PBRS_TRI_SPHERE)) {
+                    // IsoBlas<Sphere>: the leaf closure is the sphere's own test (blas.rs:267-274)
+                    if (COUNT) tc.spheres++;
+                    float t;
+                    if (ball_test(tv.p0, tv.p1.x, ray, ANY, t)) {
+                        if (ANY) { occluded = true; done = true; return; }
+                        if (t < l_best_t) { l_best_t = t; l_best_tri = s; }
+                    }
+                } else if (ANY) {
+                    if (COUNT) tc.tris++;
                     if (tri_occludes(tv.p0, tv.p1, tv.p2, ray, dg)) { occluded = true; done = true; return; }
                 } else {
+                    if (COUNT) tc.tris++;
                     float t;
                     bool hit;
                     if (tv.flags & PBRS_TRI_CHECK_SHADING) {
@@ -286,15 +298,23 @@ struct Walk {
         uint32_t kind, index;
         Ray obj = to_object(sc.inst_trav + first, wr, kind, index);
         if (!(len2(obj.d) > (ANY ? 1e-6f : 1e-3f))) flag(dg, P_MISC);
-        if (kind == PBRS_SHAPE_SPHERE) {
-            if (COUNT) tc.spheres++;
-            f4 s = ld16(sc.spheres + index);
+        if (kind != PBRS_SHAPE_MESH) {
+            float t = PB_INF;
+            bool hit;
+            if (kind == PBRS_SHAPE_SPHERE) {
+                if (COUNT) tc.spheres++;
+                f4 s = ld16(sc.spheres + index);
+                hit = ANY ? sphere_occludes(mk(s.x, s.y, s.z), s.w, obj) : sphere_hit_t(mk(s.x, s.y, s.z), s.w, obj, t);
+            } else if (!EXT) {
+                hit = false;  // unreachable: has_ext selects the EXT kernels
+            } else {  // quad, cuboid, disk: shape/src/simple.rs
+                hit = ANY ? simple_occludes(sc.simples + index, kind, obj) : simple_hit_t(sc.simples + index, kind, obj, t, dg);
+            }
             if (ANY) {
-                if (sphere_occludes(mk(s.x, s.y, s.z), s.w, obj)) { occluded = true; done = true; }
+                if (hit) { occluded = true; done = true; }
                 return;
             }
-            float t;
-            if (sphere_hit_t(mk(s.x, s.y, s.z), s.w, obj, t)) {
+            if (hit) {
                 ret = t;
                 if (t <= best.t) { best.t = t; best.inst = first; best.tri = 0u; }
             } else {

@@ -1,7 +1,7 @@
 // pbrs_main -- the reference's driver (src/main.rs:56-246) with the B200 back end behind it.
 //
 //   pbrs_main --pbrt_file scene.pbrt [--integrator direct|path] [--msaa N]
-//   pbrs_main --scene_name cornell_box|125_spheres ...
+//   pbrs_main --scene_name cornell_box|cornell_box_mesh|125_spheres|quad|quad_light ...
 //
 // Same command-line keys as src/cli_options.rs:52-59 (--use_multi_thread / --use_single_thread are
 // accepted and ignored: there is one GPU path; --visualize_* are debug views outside the hot path).
@@ -16,6 +16,7 @@
 #include <string>
 
 #include "../../../include/pbrs_gpu.hpp"
+#include "../../../include/pbrs_presets.hpp"
 #include "../../../include/pbrs_scene_file.hpp"
 
 using namespace pbrs;
@@ -53,59 +54,6 @@ bool parse_args(int argc, char **argv, CliOptions &o, std::string &err) {  // :6
     return true;
 }
 
-ShapeRef quad(Point3 a, Point3 b, Point3 c, Point3 d) {
-    return shape::TriangleMesh::from_soa({a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z}, {}, {}, {0, 1, 2, 0, 2, 3});
-}
-ShapeRef box(Point3 lo, Point3 hi) {
-    std::vector<float> P = {lo.x, lo.y, lo.z, hi.x, lo.y, lo.z, hi.x, hi.y, lo.z, lo.x, hi.y, lo.z, lo.x, lo.y, hi.z, hi.x, lo.y, hi.z, hi.x, hi.y, hi.z, lo.x, hi.y, hi.z};
-    const uint32_t q[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 5, 4}, {3, 2, 6, 7}, {0, 3, 7, 4}, {1, 2, 6, 5}};
-    std::vector<uint32_t> idx;
-    for (auto &f : q) { idx.insert(idx.end(), {f[0], f[1], f[2]}); idx.insert(idx.end(), {f[0], f[2], f[3]}); }
-    return shape::TriangleMesh::from_soa(P, {}, {}, idx);
-}
-
-// preset::cornell_box (scene/src/preset.rs:194-257) with triangle walls and a sphere light: the
-// reference's own uses ParallelQuad / Cuboid and a quad light, on which it panics.
-Scene cornell_box() {
-    Camera camera({600, 600}, Angle::new_deg(40.0f));
-    camera.look_at(point3(278, 278, -800), point3(278, 278, 0), Vec3::Y());
-    MaterialRef red = mtl::Lambertian::solid({0.65f, 0.05f, 0.05f}), white = mtl::Lambertian::solid(Color::gray(0.73f)), green = mtl::Lambertian::solid({0.12f, 0.45f, 0.15f});
-    const Color L{15, 15, 15};
-    const float S = 555.0f;
-    std::vector<Instance> inst = {
-        Instance(quad({S, 0, 0}, {S, S, 0}, {S, S, S}, {S, 0, S}), green), Instance(quad({0, 0, 0}, {0, S, 0}, {0, S, S}, {0, 0, S}), red),
-        Instance(quad({0, 0, 0}, {S, 0, 0}, {S, 0, S}, {0, 0, S}), white), Instance(quad({0, S, 0}, {S, S, 0}, {S, S, S}, {0, S, S}), white),
-        Instance(quad({0, 0, S}, {S, 0, S}, {S, S, S}, {0, S, S}), white),
-        Instance(box({0, 0, 0}, {165, 165, 165}), white).with_transform(AffineTransform::translater({265, 0, 105}) * AffineTransform::rotater(Vec3::Y(), Angle::new_deg(15))),
-        Instance(box({0, 0, 0}, {165, 330, 165}), white).with_transform(AffineTransform::translater({130, 0, 225}) * AffineTransform::rotater(Vec3::Y(), Angle::new_deg(-18))),
-        Instance(shape::Sphere::create({0, 0, 0}, 40), mtl::DiffuseLight::create(L)).with_transform(AffineTransform::translater({278, 514, 279.5f})),
-    };
-    return Scene(std::move(inst), camera).with_lights({}, {light::DiffuseAreaLight(L, light::SamplableShape::Sphere({278, 514, 279.5f}, 40))});
-}
-
-// preset::mixed_spheres (scene/src/preset.rs:55-113) with a seeded generator instead of thread_rng
-Scene mixed_spheres() {
-    Camera camera({1024, 768}, Angle::new_deg(25.0f));
-    camera.look_at(point3(13, 2, 3), point3(0, 0, 0), Vec3::Y());
-    uint64_t state = 0x5EEDull;
-    auto rnd = [&]() { state = state * 6364136223846793005ull + 1442695040888963407ull; return float((state >> 40) & 0xFFFFFF) / 16777216.0f; };
-    const Color gold_r{0.143176f, 0.373096f, 1.443834f}, gold_i{3.982675f, 2.387439f, 1.602465f};
-    std::vector<Instance> inst = {
-        Instance(shape::Sphere::from_raw(0, -1000, 1, 1000), mtl::Lambertian::solid(Color::gray(0.5f))), Instance(shape::Sphere::from_raw(0, 1, 0, 1), mtl::Dielectric::create(1.5f)),
-        Instance(shape::Sphere::from_raw(-4, 1, 0, 1), mtl::Lambertian::solid({0.4f, 0.2f, 0.1f})), Instance(shape::Sphere::from_raw(4, 1, 0, 1), mtl::Metal::from_ior(gold_r, gold_i, 0.0f)),
-    };
-    for (int a = -11; a < 11; ++a)
-        for (int b = -11; b < 11; ++b) {
-            float choose = rnd(), h = rnd();
-            Point3 c{a + 0.9f * rnd(), 0.2f + h * h * h * 0.1f, b + 0.9f * rnd()};
-            float dx = c.x - 4, dy = c.y - 0.2f, dz = c.z;
-            if (std::sqrt(dx * dx + dy * dy + dz * dz) <= 0.9f) continue;
-            MaterialRef m = choose < 0.8f ? mtl::Lambertian::solid({rnd(), rnd(), rnd()}) : choose < 0.95f ? mtl::Metal::from_ior(gold_r, gold_i, rnd() * 0.5f) : mtl::Dielectric::create(1.4f);
-            inst.emplace_back(shape::Sphere::create(c, 0.2f), m);
-        }
-    return Scene(std::move(inst), camera).with_fn_env_light(light::EnvFn::BlueSky);
-}
-
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -122,9 +70,12 @@ int main(int argc, char **argv) {
                 return scene_file::build_scene(p);
             }
             scene_name = options.scene_name;
-            if (options.scene_name == "cornell_box") return cornell_box();
-            if (options.scene_name == "125_spheres") return mixed_spheres();
-            std::fprintf(stderr, "No scene file or name specified. Abort.\nAvailable scenes: 125_spheres | cornell_box\n");
+            if (options.scene_name == "cornell_box") return preset::cornell_box();
+            if (options.scene_name == "cornell_box_mesh") return preset::cornell_box_mesh();
+            if (options.scene_name == "125_spheres") return preset::mixed_spheres();
+            if (options.scene_name == "quad") return preset::quad_scene();
+            if (options.scene_name == "quad_light") return preset::quad_light();
+            std::fprintf(stderr, "No scene file or name specified. Abort.\nAvailable scenes: 125_spheres | cornell_box | cornell_box_mesh | quad | quad_light\n");
             std::exit(1);
         }();
         auto t0 = std::chrono::steady_clock::now();

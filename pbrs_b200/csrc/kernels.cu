@@ -90,7 +90,7 @@ constexpr int kLeafVote = PBRS_LEAF_VOTE;  // leave phase 1 once this many lanes
 #ifndef PBRS_TRACE_BLOCKS_PER_SM
 #define PBRS_TRACE_BLOCKS_PER_SM 8
 #endif
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool EXT>
 __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
     const uint32_t *count = cnt + (ANY ? PBRS_CNT_SHADOW : PBRS_CNT_EXTEND);
     uint32_t *cursor = cnt + (ANY ? PBRS_CNT_SHADOW_CURSOR : PBRS_CNT_EXTEND_CURSOR);
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
     const uint32_t n = *count;
     uint32_t st_ref[PBRS_WALK_STACK], st_par[ANY ? 1 : PBRS_WALK_STACK];
     float st_tl[ANY ? 1 : PBRS_WALK_STACK];
-    Walk<ANY, COUNT> w(st_ref, st_tl, st_par);
+    Walk<ANY, COUNT, EXT> w(st_ref, st_tl, st_par);
     w.done = true; w.next = PBRS_NONE;
     bool busy = false, exhausted = false;
     uint32_t j = 0u, vis = 0u;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) k_write_samples(PathBuffers pb, Fram
 }
 
 struct Grid {
-    int extend, extend_count, shadow, shadow_count, small;
+    int extend, extend_ext, extend_count, shadow, shadow_ext, shadow_count, small;
     int shade[2][PBRS_NUM_CLS];
 };
 
@@ -345,12 +345,14 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
         w.sms = prop.multiProcessorCount;
     }
     if (!w.grid_ready) {
-        w.grid.extend = blocks_for(k_trace<false, false>, w.sms);
-        w.grid.extend_count = blocks_for(k_trace<false, true>, w.sms);
+        w.grid.extend = blocks_for(k_trace<false, false, false>, w.sms);
+        w.grid.extend_ext = blocks_for(k_trace<false, false, true>, w.sms);
+        w.grid.extend_count = blocks_for(k_trace<false, true, true>, w.sms);
         size_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, w.sms);
         size_shade<PBRS_INTEGRATOR_PATH>(w.grid, w.sms);
-        w.grid.shadow = blocks_for(k_trace<true, false>, w.sms);
-        w.grid.shadow_count = blocks_for(k_trace<true, true>, w.sms);
+        w.grid.shadow = blocks_for(k_trace<true, false, false>, w.sms);
+        w.grid.shadow_ext = blocks_for(k_trace<true, false, true>, w.sms);
+        w.grid.shadow_count = blocks_for(k_trace<true, true, true>, w.sms);
         w.grid.small = blocks_for(k_generate, w.sms);
         w.grid_ready = true;
     }
@@ -509,16 +511,18 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         for (int stage = 0; stage < n_stages; ++stage) {
             uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
             uint32_t *cnt = pb.counts + PBRS_CNT_STRIDE * stage, *next_cnt = cnt + PBRS_CNT_STRIDE;
-            if (count_trav) k_trace<false, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
-            else k_trace<false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+            if (count_trav) k_trace<false, true, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+            else if (sc.has_ext) k_trace<false, false, true><<<w.grid.extend_ext, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+            else k_trace<false, false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
             ++launches; ++launches_extend;
             mark(T_EXT);
             if (tg.only_sample >= 0) break;
             if (o.integrator == PBRS_INTEGRATOR_PATH) launch_shade<PBRS_INTEGRATOR_PATH>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
             else launch_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
             mark(T_SHADE);
-            if (count_trav) k_trace<true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
-            else k_trace<true, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+            if (count_trav) k_trace<true, true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+            else if (sc.has_ext) k_trace<true, false, true><<<w.grid.shadow_ext, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+            else k_trace<true, false, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
             mark(T_SHADOW);
             launches += PBRS_NUM_CLS + 1; ++launches_shadow;
         }

@@ -47,6 +47,8 @@ static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
 // (shape/src/blas.rs:193-201); the traversal must evaluate the shading interpolation for it.
 #define PBRS_TRI_CHECK_SHADING 1u
 #define PBRS_TRI_LAST_IN_LEAF 2u
+// The record is a sphere of an IsoBlas<Sphere> (shape/src/blas.rs:36-70): p0 = centre, p1[0] = radius.
+#define PBRS_TRI_SPHERE 4u
 
 // Shading attributes of one triangle, gathered per TRIANGLE (same index as its TriRec) instead of
 // per vertex: one dependent fetch after the hit record instead of three (index triple, then the
@@ -64,14 +66,28 @@ struct SphereRec {
 };
 static_assert(sizeof(SphereRec) == 16, "SphereRec must be 16 bytes");
 
+// ParallelQuad / Cuboid / Disk (shape/src/simple.rs:33-182): three float3 each.
+//   quad:   a = origin, b = side_u, c = side_v
+//   cuboid: a = min,    b = max
+//   disk:   a = centre, b = normal (unit), c = radial
+struct SimpleRec {
+    float a[3]; uint32_t pad0;
+    float b[3]; uint32_t pad1;
+    float c[3]; uint32_t pad2;
+};
+static_assert(sizeof(SimpleRec) == 48, "SimpleRec must be 48 bytes");
+
 #define PBRS_SHAPE_SPHERE 0u
-#define PBRS_SHAPE_MESH 1u
+#define PBRS_SHAPE_MESH 1u   // a triangle mesh or a sphere BLAS (TriRec flags tell which)
+#define PBRS_SHAPE_QUAD 2u
+#define PBRS_SHAPE_CUBOID 3u
+#define PBRS_SHAPE_DISK 4u
 
 // Row r of a 3x4 matrix = (c0[r], c1[r], c2[r], c3[r]) of the reference's column Mat4.
 struct InstTravRec {
     float inv[3][4];
     uint32_t shape_kind;
-    uint32_t shape_index;  // sphere record index / mesh header index
+    uint32_t shape_index;  // sphere / simple-shape record index, or mesh header index
     uint32_t identity;     // fwd == inv == I (add_instance got NULL matrices)
     uint32_t pad;
 };
@@ -139,6 +155,8 @@ struct DeltaLightRec {
 };
 #define PBRS_AREA_SPHERE 0
 #define PBRS_AREA_TRIANGLE 1
+#define PBRS_AREA_QUAD 2      // p0 = origin, p1 = side_u, p2 = side_v
+#define PBRS_AREA_DISK 3      // p0 = centre, p1 = normal (unit), p2 = radial
 struct AreaLightRec {
     int32_t kind;
     float p0[3];  // sphere: centre
@@ -166,6 +184,7 @@ struct DeviceScene {
     const NodeRec *blas_nodes;
     const TriRec *tris;
     const SphereRec *spheres;
+    const SimpleRec *simples;   // quads, cuboids and disks
     const InstTravRec *inst_trav;
     const InstShadeRec *inst_shade;
     const MeshRec *meshes;
@@ -186,6 +205,7 @@ struct DeviceScene {
     float tlas_min[3], tlas_max[3];
     uint32_t tlas_root_is_leaf;  // a single instance
     uint32_t n_instances;
+    uint32_t has_ext;  // any quad / cuboid / disk instance or sphere BLAS: selects the EXT traversal kernels
 };
 
 }  // namespace pbrs

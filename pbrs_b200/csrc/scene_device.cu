@@ -72,6 +72,7 @@ int device_upload(SceneImpl &s) {
     if ((rc = upload(d, f.blas_nodes, ds.blas_nodes)) < 0) return rc;
     if ((rc = upload(d, f.tris, ds.tris)) < 0) return rc;
     if ((rc = upload(d, s.spheres, ds.spheres)) < 0) return rc;
+    if ((rc = upload(d, s.simples, ds.simples)) < 0) return rc;
     if ((rc = upload(d, f.trav, ds.inst_trav)) < 0) return rc;
     if ((rc = upload(d, f.shade, ds.inst_shade)) < 0) return rc;
     if ((rc = upload(d, f.meshes, ds.meshes)) < 0) return rc;

@@ -243,6 +243,26 @@ inline void v_hat(const float *a, float *o) {  // Vec3::hat, math/src/hcm.rs:112
 
 // Can TriangleMesh::intersect_triangle's tangent check (blas.rs:193-201) ever reject a hit on
 // this triangle?  Conservative (double precision, wide margins): returns true = "maybe".
+inline HostBox sphere_box(const SphereRec &sp) {  // Sphere::bbox, shape/src/simple.rs:203-206
+    float hd[3] = {1.0f * sp.r, 1.0f * sp.r, 1.0f * sp.r};
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = sp.c[k] - hd[k]; hi[k] = sp.c[k] + hd[k]; }
+    return box_of_points(lo, hi);
+}
+// make_coord_system, math/src/hcm.rs:595-605 (abs_min_dimension :165-176)
+inline void host_make_coord_system(const float v[3], float o1[3], float o2[3]) {
+    float ax = std::fabs(v[0]), ay = std::fabs(v[1]), az = std::fabs(v[2]);
+    int i0 = ax < ay ? 0 : 1;
+    i0 = (i0 == 0 ? ax : ay) < az ? i0 : 2;
+    int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+    float v1[3] = {0.0f, 0.0f, 0.0f}, v2[3];
+    v1[i1] = v[i2];
+    v1[i2] = -v[i1];
+    v_cross(v, v1, v2);
+    v_hat(v1, o1);
+    v_hat(v2, o2);
+}
+
 bool tri_may_reject(const HostMesh &m, uint32_t t) {
     uint32_t i = m.idx[3 * t], k = m.idx[3 * t + 1], j = m.idx[3 * t + 2];
     auto P = [&](uint32_t v, int c) { return (double)m.P[3 * v + c]; };
@@ -357,6 +377,62 @@ int host_add_mesh(SceneImpl &s, const float *P, const float *N, const float *UV,
     return (int)s.shapes.size() - 1;
 }
 
+// IsoBlas::<Sphere>::build, shape/src/blas.rs:60-69
+int host_add_sphere_blas(SceneImpl &s, const float *centers_radii, uint32_t n) {
+    HostMesh m;
+    m.balls.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 4; ++k)
+            if (std::isnan(centers_radii[4 * i + k])) { set_error("add_sphere_blas: NaN (Sphere::from_raw asserts, shape/src/simple.rs:21-22)"); return PBRS_ERR_INVALID_ARG; }
+        for (int k = 0; k < 3; ++k) m.balls[i].c[k] = centers_radii[4 * i + k];
+        m.balls[i].r = centers_radii[4 * i + 3];
+    }
+    s.meshes.push_back(std::move(m));
+    s.shapes.push_back(HostShape{PBRS_SHAPE_MESH, (uint32_t)s.meshes.size() - 1});
+    return (int)s.shapes.size() - 1;
+}
+
+int host_add_simple(SceneImpl &s, uint32_t kind, const float a[3], const float b[3], const float c[3]) {
+    SimpleRec r;
+    std::memset(&r, 0, sizeof r);
+    for (int k = 0; k < 3; ++k) { r.a[k] = a[k]; r.b[k] = b[k]; r.c[k] = c ? c[k] : 0.0f; }
+    s.simples.push_back(r);
+    s.shapes.push_back(HostShape{kind, (uint32_t)s.simples.size() - 1});
+    return (int)s.shapes.size() - 1;
+}
+
+// Disk::new, shape/src/simple.rs:42-52: normalises the normal; its two asserts are argument errors.
+int host_make_disk(const float center[3], const float normal[3], const float radial[3], float out_normal[3]) {
+    (void)center;
+    float n2 = v_dot(normal, normal);
+    if (!(n2 != 0.0f && std::isfinite(n2))) { set_error("disk: the normal cannot be normalised"); return PBRS_ERR_INVALID_ARG; }
+    v_hat(normal, out_normal);
+    float r2 = v_dot(radial, radial);
+    if (!std::isfinite(r2)) { set_error("disk: radial is not finite (simple.rs:44)"); return PBRS_ERR_INVALID_ARG; }
+    if (!(std::fabs(v_dot(radial, out_normal)) < 1e-6f)) { set_error("disk: radial is not perpendicular to the normal (simple.rs:45)"); return PBRS_ERR_INVALID_ARG; }
+    return 0;
+}
+
+// Shape::bbox of the simple shapes in object space.
+static HostBox simple_box(uint32_t kind, const SimpleRec &r) {
+    if (kind == PBRS_SHAPE_QUAD) {  // simple.rs:105-113
+        float ou[3], ov[3], ouv[3];
+        for (int k = 0; k < 3; ++k) { ou[k] = r.a[k] + r.b[k]; ov[k] = r.a[k] + r.c[k]; ouv[k] = r.a[k] + r.b[k] + r.c[k]; }
+        return box_merge(box_of_points(r.a, ou), box_of_points(ov, ouv));
+    }
+    if (kind == PBRS_SHAPE_CUBOID) return box_of_points(r.a, r.b);  // :339-341
+    // Disk, :298-305: make_coord_system(normal) scaled by |radial|
+    float v1[3], v2[3];
+    host_make_coord_system(r.b, v1, v2);
+    float rn = std::sqrt(v_dot(r.c, r.c));
+    float p[4][3];
+    for (int k = 0; k < 3; ++k) {
+        float a = v1[k] * rn, b = v2[k] * rn;
+        p[0][k] = r.a[k] + a + b; p[1][k] = r.a[k] + a - b; p[2][k] = r.a[k] - a - b; p[3][k] = r.a[k] - a + b;
+    }
+    return box_merge(box_of_points(p[0], p[1]), box_of_points(p[2], p[3]));
+}
+
 int host_add_instance(SceneImpl &s, int shape, int mtl, const float *fwd, const float *inv) {
     HostInstance in;
     in.shape = shape;
@@ -382,9 +458,11 @@ int host_build(SceneImpl &s) {
     // ---- BLAS per mesh ----
     uint32_t total_nodes = 0, total_tris = 0;
     for (HostMesh &m : s.meshes) {
-        size_t nt = m.idx.size() / 3;
+        const bool is_balls = !m.balls.empty();
+        size_t nt = is_balls ? m.balls.size() : m.idx.size() / 3;
         std::vector<HostBox> boxes(nt);
-        for (size_t t = 0; t < nt; ++t) {  // blas.rs:141: BBox::new(p[i], p[j]).union(p[k])
+        for (size_t t = 0; is_balls && t < nt; ++t) boxes[t] = sphere_box(m.balls[t]);  // blas.rs:66: |s| s.bbox()
+        for (size_t t = 0; !is_balls && t < nt; ++t) {  // blas.rs:141: BBox::new(p[i], p[j]).union(p[k])
             const float *pi = &m.P[3 * m.idx[3 * t]], *pj = &m.P[3 * m.idx[3 * t + 1]], *pk = &m.P[3 * m.idx[3 * t + 2]];
             HostBox b = box_of_points(pi, pj);
             box_grow_point(b, pk);
@@ -406,12 +484,10 @@ int host_build(SceneImpl &s) {
     for (HostInstance &in : s.instances) {
         const HostShape &sh = s.shapes[in.shape];
         HostBox sb;
-        if (sh.kind == PBRS_SHAPE_SPHERE) {  // shape/src/simple.rs:203-206
-            const SphereRec &sp = s.spheres[sh.index];
-            float hd[3] = {1.0f * sp.r, 1.0f * sp.r, 1.0f * sp.r};
-            float lo[3], hi[3];
-            for (int k = 0; k < 3; ++k) { lo[k] = sp.c[k] - hd[k]; hi[k] = sp.c[k] + hd[k]; }
-            sb = box_of_points(lo, hi);
+        if (sh.kind == PBRS_SHAPE_SPHERE) {
+            sb = sphere_box(s.spheres[sh.index]);
+        } else if (sh.kind != PBRS_SHAPE_MESH) {
+            sb = simple_box(sh.kind, s.simples[sh.index]);
         } else {
             sb = s.meshes[sh.index].root_box;
         }
@@ -463,14 +539,24 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
         for (int k = 0; k < 3; ++k) { r.bmin[k] = m.root_box.mn[k]; r.bmax[k] = m.root_box.mx[k]; }
         r.node_base = (uint32_t)blas_nodes.size();
         r.tri_base = (uint32_t)tris.size();
-        r.n_tris = (uint32_t)(m.idx.size() / 3);
+        r.n_tris = (uint32_t)m.order.size();
         r.root_is_leaf = m.root_is_leaf ? 1u : 0u;
         meshes.push_back(r);
         blas_nodes.insert(blas_nodes.end(), m.nodes.begin(), m.nodes.end());
         size_t t0 = tris.size();
         tris.resize(t0 + m.order.size());
         tri_shade.resize(t0 + m.order.size());
-        for (size_t q = 0; q < m.order.size(); ++q) {
+        for (size_t q = 0; q < m.order.size() && !m.balls.empty(); ++q) {
+            uint32_t t = m.order[q];
+            TriRec &tr = tris[t0 + q];
+            std::memset(&tr, 0, sizeof tr);
+            for (int c = 0; c < 3; ++c) tr.p0[c] = m.balls[t].c[c];
+            tr.p1[0] = m.balls[t].r;
+            tr.orig = t;
+            tr.flags = PBRS_TRI_SPHERE;
+            std::memset(&tri_shade[t0 + q], 0, sizeof(TriShadeRec));
+        }
+        for (size_t q = 0; q < m.order.size() && m.balls.empty(); ++q) {
             uint32_t t = m.order[q];
             // (i, k, j) = index_triple, shape/src/blas.rs:162-163
             uint32_t i = m.idx[3 * t], k = m.idx[3 * t + 1], j = m.idx[3 * t + 2];
@@ -551,6 +637,9 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     for (int k = 0; k < 3; ++k) { ds.tlas_min[k] = s.tlas_box.mn[k]; ds.tlas_max[k] = s.tlas_box.mx[k]; }
     ds.tlas_root_is_leaf = s.tlas_root_is_leaf ? 1u : 0u;
     ds.n_instances = (uint32_t)s.instances.size();
+    ds.has_ext = s.simples.empty() ? 0u : 1u;
+    for (const HostMesh &m : s.meshes)
+        if (!m.balls.empty()) ds.has_ext = 1u;
 }
 
 }  // namespace pbrs

@@ -18,6 +18,7 @@ struct HostBox {
 struct HostMesh {
     std::vector<float> P, N, UV;      // nverts*3, nverts*3, nverts*2
     std::vector<uint32_t> idx;        // ntris*3 (caller order)
+    std::vector<SphereRec> balls;     // IsoBlas<Sphere>: the primitives are these spheres; P/N/UV/idx stay empty
     // build output
     std::vector<NodeRec> nodes;       // inner nodes, preorder, indices relative to this mesh
     std::vector<uint32_t> order;      // triangle ids in leaf order
@@ -29,7 +30,7 @@ struct HostMesh {
 
 struct HostShape {
     uint32_t kind;   // PBRS_SHAPE_*
-    uint32_t index;  // into spheres / meshes
+    uint32_t index;  // into spheres / simples / meshes
 };
 
 struct HostInstance {
@@ -56,6 +57,7 @@ struct SceneImpl {
     std::vector<MaterialRec> materials;
     std::vector<HostShape> shapes;
     std::vector<SphereRec> spheres;
+    std::vector<SimpleRec> simples;   // quads, cuboids, disks (HostShape::kind tells which)
     std::vector<HostMesh> meshes;
     std::vector<HostInstance> instances;
     std::vector<DeltaLightRec> delta_lights;
@@ -101,6 +103,9 @@ const char *get_error();
 // scene_host.cpp
 int host_set_camera(SceneImpl &s, uint32_t w, uint32_t h, float fov, const float *eye, const float *target, const float *up);
 int host_add_mesh(SceneImpl &s, const float *P, const float *N, const float *UV, uint32_t nverts, const uint32_t *idx, uint32_t ntris);
+int host_add_sphere_blas(SceneImpl &s, const float *centers_radii, uint32_t n);
+int host_add_simple(SceneImpl &s, uint32_t kind, const float a[3], const float b[3], const float c[3]);
+int host_make_disk(const float center[3], const float normal[3], const float radial[3], float out_normal[3]);
 int host_add_instance(SceneImpl &s, int shape, int mtl, const float *fwd, const float *inv);
 int host_build(SceneImpl &s);  // BLAS per mesh, instance boxes, TLAS; fills tlas_nodes etc.
 bool host_tri_may_reject(const HostMesh &m, uint32_t t);

@@ -18,6 +18,10 @@ def _f3(v):
     return a, a.ctypes.data_as(K.c_float_p)
 
 
+def _f32s(pair):
+    return np.float32(pair[0]), np.float32(pair[1])
+
+
 class PbrsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"pbrs error {code}: {msg}")
@@ -113,6 +117,42 @@ class SceneDesc:
         self.n_shape += 1
         return self.n_shape - 1
 
+    def add_quad(self, origin, side_u, side_v):
+        """ParallelQuad{origin, side_u, side_v} (shape/src/simple.rs:69-74)."""
+        self.ops.append(("scene_add_quad", (origin, side_u, side_v)))
+        self.n_shape += 1
+        return self.n_shape - 1
+
+    # ParallelQuad::new_xy / new_xz / new_yz, shape/src/simple.rs:76-102 (differences in f32)
+    def add_quad_xy(self, x_range, y_range, z):
+        (x0, x1), (y0, y1) = _f32s(x_range), _f32s(y_range)
+        return self.add_quad((x0, y0, z), (x1 - x0, 0.0, 0.0), (0.0, y1 - y0, 0.0))
+
+    def add_quad_xz(self, x_range, y, z_range):
+        (x0, x1), (z0, z1) = _f32s(x_range), _f32s(z_range)
+        return self.add_quad((x0, y, z0), (x1 - x0, 0.0, 0.0), (0.0, 0.0, z1 - z0))
+
+    def add_quad_yz(self, x, y_range, z_range):
+        (y0, y1), (z0, z1) = _f32s(y_range), _f32s(z_range)
+        return self.add_quad((x, y0, z0), (0.0, 0.0, z1 - z0), (0.0, y1 - y0, 0.0))
+
+    def add_cuboid(self, p0, p1):
+        self.ops.append(("scene_add_cuboid", (p0, p1)))
+        self.n_shape += 1
+        return self.n_shape - 1
+
+    def add_disk(self, center, normal, radial):
+        self.ops.append(("scene_add_disk", (center, normal, radial)))
+        self.n_shape += 1
+        return self.n_shape - 1
+
+    def add_sphere_blas(self, centers_radii):
+        """IsoBlas::<Sphere>::build: an (n, 4) array of (cx, cy, cz, radius)."""
+        cr = np.ascontiguousarray(centers_radii, dtype=np.float32).reshape(-1, 4)
+        self.ops.append(("scene_add_sphere_blas", (cr,)))
+        self.n_shape += 1
+        return self.n_shape - 1
+
     def add_instance(self, shape, mtl, fwd=None, inv=None):
         """fwd/inv: 4x4 numpy matrices in the usual math (row, col) convention, or None."""
         if fwd is not None:
@@ -135,6 +175,12 @@ class SceneDesc:
 
     def add_area_light_triangle(self, p0, p1, p2, emit):
         self.ops.append(("scene_add_area_light_triangle", (p0, p1, p2, emit)))
+
+    def add_area_light_quad(self, origin, side_u, side_v, emit):
+        self.ops.append(("scene_add_area_light_quad", (origin, side_u, side_v, emit)))
+
+    def add_area_light_disk(self, center, normal, radial, emit):
+        self.ops.append(("scene_add_area_light_disk", (center, normal, radial, emit)))
 
     # -- environment --
     def set_env_constant(self, rgb):
@@ -177,6 +223,9 @@ class SceneDesc:
                 Pm, Nm, UVm, idx = args
                 rc = fn(h.ptr, Pm.ctypes.data_as(K.c_float_p), Nm.ctypes.data_as(K.c_float_p),
                         UVm.ctypes.data_as(K.c_float_p), Pm.shape[0], idx.ctypes.data_as(K.c_u32_p), idx.shape[0])
+            elif name == "scene_add_sphere_blas":
+                cr = args[0]
+                rc = fn(h.ptr, cr.ctypes.data_as(K.c_float_p), cr.shape[0])
             elif name == "scene_add_instance":
                 shape, mtl, fwd, inv = args
                 if fwd is None:

@@ -106,6 +106,135 @@ def cornell_box(width=512, height=512):
     return sd
 
 
+def _rotate_y_translate(deg, t):
+    """identity().rotate_y(deg).translate(t) in the reference's own FP32 arithmetic
+    (geometry/src/transform.rs:169-179): forward and inverse composed side by side."""
+    from .pbrt_loader import Affine, _to_radians
+    return Affine.translater(t) * Affine.rotater((0.0, 1.0, 0.0), _to_radians(deg))
+
+
+def preset_cornell_box(width=600, height=600):
+    """scene/src/preset.rs:194-257 as written: six ParallelQuads, two Cuboids under rotate_y +
+    translate, one quad area light (Q11: under the path integrator the reference itself panics
+    on this scene once a BSDF sample reaches the light's mirrored extension; those samples are
+    counted in would_panic['quad'] here)."""
+    sd = SceneDesc()
+    sd.set_camera(width, height, 40.0, (278.0, 278.0, -800.0), (278.0, 278.0, 0.0), (0, 1, 0))
+    red = sd.lambertian((0.65, 0.05, 0.05))
+    white = sd.lambertian((0.73, 0.73, 0.73))
+    green = sd.lambertian((0.12, 0.45, 0.15))
+    L = (15.0, 15.0, 15.0)
+    light = sd.diffuse_light(L)
+    shapes = [
+        sd.add_quad_yz(555.0, (0.0, 555.0), (0.0, 555.0)),
+        sd.add_quad_yz(0.0, (0.0, 555.0), (0.0, 555.0)),
+        sd.add_quad_xz((213.0, 343.0), 554.0, (227.0, 332.0)),
+        sd.add_quad_xz((0.0, 555.0), 0.0, (0.0, 555.0)),
+        sd.add_quad_xz((0.0, 555.0), 555.0, (0.0, 555.0)),
+        sd.add_quad_xy((0.0, 555.0), (0.0, 555.0), 555.0),
+        sd.add_cuboid((0.0, 0.0, 0.0), (165.0, 165.0, 165.0)),
+        sd.add_cuboid((0.0, 0.0, 0.0), (165.0, 330.0, 165.0)),
+    ]
+    mtls = [red, green, light, white, white, white, white, white]  # mtl_seq, preset.rs:230-232
+    xf = {6: _rotate_y_translate(15.0, (265.0, 0.0, 105.0)), 7: _rotate_y_translate(-18.0, (130.0, 0.0, 225.0))}
+    for i, (sh, m) in enumerate(zip(shapes, mtls)):
+        t = xf.get(i)
+        sd.add_instance(sh, m, fwd=t and t.fwd, inv=t and t.inv)
+    sd.add_area_light_quad((213.0, 554.0, 227.0), (343.0 - 213.0, 0.0, 0.0), (0.0, 0.0, 332.0 - 227.0), L)
+    return sd
+
+
+def preset_quad(width=800, height=800):
+    """scene/src/preset.rs:184-192: one quad under the blue sky, camera at its default pose."""
+    sd = SceneDesc()
+    # Camera::new without look_at (geometry/src/camera.rs:19-33): at the origin, identity
+    # orientation = looking down +z, which look_at(origin -> +z, up = y) reproduces exactly
+    sd.set_camera(width, height, 45.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0, 1, 0))
+    sd.add_instance(sd.add_quad_xy((-0.5, 0.5), (-0.3, 0.6), 2.5), sd.lambertian((0.2, 0.3, 0.7)))
+    sd.set_env_fn(K.ENV_BLUE_SKY)
+    return sd
+
+
+def preset_quad_light(width=800, height=800, seed=SEED):
+    """scene/src/preset.rs:148-182: two perlin spheres lit by a quad light and a sphere light."""
+    sd = SceneDesc()
+    sd.set_camera(width, height, 20.0, (26.0, 3.0, -6.0), (0.0, 2.0, 0.0), (0, 1, 0))
+    rv, px, py, pz = perlin_tables(seed)
+    mtl = sd.lambertian(tex=sd.add_texture_perlin(4.0, rv, px, py, pz))
+    L = (4.0, 4.0, 4.0)
+    light = sd.diffuse_light(L)
+    sd.add_instance(sd.add_sphere((0.0, -1000.0, 0.0), 1000.0), mtl)
+    sd.add_instance(sd.add_sphere((0.0, 2.0, 0.0), 2.0), mtl)
+    sd.add_instance(sd.add_quad_xy((3.0, 5.0), (1.0, 3.0), 2.1), light)
+    sd.add_instance(sd.add_sphere((0.0, 7.0, 0.0), 2.0), light)
+    sd.add_area_light_quad((3.0, 1.0, 2.1), (2.0, 0.0, 0.0), (0.0, 2.0, 0.0), L)
+    sd.add_area_light_sphere((0.0, 7.0, 0.0), 2.0, L)
+    sd.set_env_fn(K.ENV_DARK_ROOM)
+    return sd
+
+
+def preset_everything(width=800, height=800, n_balls=1000, n_boxes=20, seed=SEED):
+    """scene/src/preset.rs:360-442 (seeded instead of OS-random, a generated image for
+    assets/earthmap.png): a floor of random-height cuboids, a quad light, glass / metal / textured
+    spheres and a rotated IsoBlas of `n_balls` small spheres."""
+    rng = np.random.default_rng(seed)
+    sd = SceneDesc()
+    sd.set_camera(width, height, 40.0, (478.0, 278.0, -600.0), (278.0, 278.0, 0.0), (0, 1, 0))
+    ground = sd.lambertian((0.48, 0.83, 0.53))
+    w = 100.0 * 20 / n_boxes
+    for i in range(n_boxes):
+        for j in range(n_boxes):
+            x0, z0 = -1000.0 + i * w, -1000.0 + j * w
+            y1 = float(rng.uniform(1.0, 101.0))
+            sd.add_instance(sd.add_cuboid((x0, 0.0, z0), (x0 + w, y1, z0 + w)), ground)
+    L = (7.0, 7.0, 7.0)
+    sd.add_instance(sd.add_quad_xz((123.0, 423.0), 554.0, (147.0, 412.0)), sd.diffuse_light(L))
+    sd.add_area_light_quad((123.0, 554.0, 147.0), (300.0, 0.0, 0.0), (0.0, 0.0, 265.0), L)
+    sd.add_instance(sd.add_sphere((400.0, 400.0, 200.0), 50.0), sd.lambertian((0.7, 0.3, 0.1)))
+    sd.add_instance(sd.add_sphere((260.0, 150.0, 45.0), 50.0), sd.dielectric(1.5))
+    sd.add_instance(sd.add_sphere((0.0, 150.0, 145.0), 50.0), sd.metal(SILVER[0], SILVER[1], 1.0))
+    sd.add_instance(sd.add_sphere((360.0, 150.0, 145.0), 70.0), sd.dielectric(1.5))
+    sd.add_instance(sd.add_sphere((400.0, 200.0, 400.0), 100.0),
+                    sd.lambertian(tex=sd.add_texture_image(checker_noise_image(256, seed))))
+    rv, px, py, pz = perlin_tables(seed)
+    sd.add_instance(sd.add_sphere((220.0, 280.0, 300.0), 80.0), sd.lambertian(tex=sd.add_texture_perlin(10.0, rv, px, py, pz)))
+    balls = np.concatenate([rng.uniform(0.0, 165.0, (n_balls, 3)), np.full((n_balls, 1), 10.0)], axis=1)
+    t = _rotate_y_translate(15.0, (-100.0, 270.0, 395.0))
+    sd.add_instance(sd.add_sphere_blas(balls), sd.lambertian((0.73, 0.73, 0.73)), fwd=t.fwd, inv=t.inv)
+    sd.set_env_fn(K.ENV_DARK_ROOM)
+    return sd
+
+
+def shape_zoo(width=128, height=96, seed=SEED):
+    """Every Shape of shape/src/simple.rs and both BLAS kinds in one small scene, plus a disk and a
+    quad area light: the parity fixture of the simple-shape code."""
+    rng = np.random.default_rng(seed)
+    sd = SceneDesc()
+    sd.set_camera(width, height, 50.0, (0.0, 3.0, -9.0), (0.0, 1.0, 0.0), (0, 1, 0))
+    grey = sd.lambertian((0.6, 0.6, 0.6))
+    sd.add_instance(sd.add_quad_xz((-6.0, 6.0), 0.0, (-4.0, 6.0)), grey)                      # floor
+    sd.add_instance(sd.add_quad((-6.0, 0.0, 6.0), (12.0, 0.0, 0.0), (1.5, 5.0, 0.5)), sd.lambertian((0.3, 0.4, 0.7)))  # slanted back
+    sd.add_instance(sd.add_cuboid((-4.0, 0.0, 1.0), (-2.5, 1.5, 2.5)), sd.plastic((0.7, 0.2, 0.2), (0.3, 0.3, 0.3), 0.1),
+                    fwd=translate((0.3, 0.0, 0.0)) @ rotate_y(20.0))
+    sd.add_instance(sd.add_cuboid((2.0, 0.0, -1.0), (3.0, 2.5, 0.0)), sd.dielectric(1.5))
+    sd.add_instance(sd.add_disk((0.0, 0.02, -1.0), (0.0, 2.0, 0.0), (1.2, 0.0, 0.0)), sd.metal(GOLD[0], GOLD[1], 0.3))
+    sd.add_instance(sd.add_disk((0.5, 1.2, 3.0), (0.3, 0.2, -1.0), (0.0, 1.0, 0.2)),
+                    sd.lambertian(tex=sd.add_texture_image(checker_noise_image(64, seed))),
+                    fwd=translate((0.0, 0.3, 0.0)) @ scale(1.2))
+    balls = np.concatenate([rng.uniform(-1.0, 1.0, (60, 3)) * (1.5, 0.8, 1.0) + (0.0, 1.6, 1.0), rng.uniform(0.08, 0.25, (60, 1))], axis=1)
+    sd.add_instance(sd.add_sphere_blas(balls), sd.glossy((0.8, 0.7, 0.3), 0.2), fwd=translate((0.0, 0.0, 0.5)) @ rotate_y(-25.0))
+    sd.add_instance(sd.add_sphere((-1.5, 0.6, -1.5), 0.6), sd.mirror((0.9, 0.9, 0.9)))
+    Lq, Ld = (12.0, 11.0, 10.0), (20.0, 20.0, 25.0)
+    qo, qu, qv = (-1.0, 4.5, 0.0), (2.0, 0.0, 0.0), (0.0, 0.0, 1.5)
+    sd.add_instance(sd.add_quad(qo, qu, qv), sd.diffuse_light(Lq))
+    sd.add_area_light_quad(qo, qu, qv, Lq)
+    dc, dn, dr = (4.0, 3.0, 1.0), (-1.0, -0.5, 0.0), (0.0, 0.0, 0.6)
+    sd.add_instance(sd.add_disk(dc, dn, dr), sd.diffuse_light(Ld))
+    sd.add_area_light_disk(dc, dn, dr, Ld)
+    sd.set_env_constant((0.02, 0.02, 0.03))
+    return sd
+
+
 def cornell_box_pbrt(width=512, height=512):
     """The same Cornell box as pbrt-v3-subset TEXT, the form BASELINE configs[0] names ("via
     scene_parser"): LookAt / Camera / Film, matte materials, `trianglemesh` walls and boxes under

@@ -37,7 +37,7 @@ int device_upload(SceneImpl &s) {
     DeviceScene &ds = s.dscene;
     std::memset(&ds, 0, sizeof ds);
     ds.tlas_nodes = s.tlas_nodes.data(); ds.blas_nodes = f.blas_nodes.data(); ds.tris = f.tris.data();
-    ds.spheres = s.spheres.data(); ds.inst_trav = f.trav.data(); ds.inst_shade = f.shade.data(); ds.meshes = f.meshes.data();
+    ds.spheres = s.spheres.data(); ds.simples = s.simples.data(); ds.inst_trav = f.trav.data(); ds.inst_shade = f.shade.data(); ds.meshes = f.meshes.data();
     ds.tri_shade = f.tri_shade.data();
     ds.materials = s.materials.data(); ds.textures = f.textures.data(); ds.texels = f.texels.data();
     ds.perlin_vec = f.perlin_vec.data(); ds.perlin_perm = f.perlin_perm.data();

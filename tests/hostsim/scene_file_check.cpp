@@ -1,8 +1,12 @@
-// TEST TOOLING: loads a pbrt-subset file with the C++ loader (include/pbrs_scene_file.hpp), commits it
+// TEST TOOLING: loads a pbrt-subset file with the C++ loader (include/pbrs_scene_file.hpp) or builds a
+// C++ preset ("preset:<name>", include/pbrs_presets.hpp), commits it
 // through the host build (libhostsim.so exports the product's pbrs_scene_* entry points) and dumps
 // scene facts + the primary-hit ids, for comparison with the Python loader (tests/test_scene_io.py).
 #include <cstdio>
 
+#include <string>
+
+#include "../../include/pbrs_presets.hpp"
 #include "../../include/pbrs_scene_file.hpp"
 
 extern "C" int hostsim_render_ids(const pbrs_scene *, const pbrs_render_opts *, uint32_t, uint32_t *, uint32_t *, float *);
@@ -10,7 +14,12 @@ extern "C" int hostsim_render_ids(const pbrs_scene *, const pbrs_render_opts *, 
 int main(int argc, char **argv) {
     if (argc < 3) return 2;
     try {
-        pbrs::Scene sc = pbrs::scene_file::build_scene(argv[1]);
+        const std::string what = argv[1];
+        pbrs::Scene sc = what == "preset:cornell_box" ? pbrs::preset::cornell_box()
+                         : what == "preset:quad" ? pbrs::preset::quad_scene()
+                         : what == "preset:quad_light" ? pbrs::preset::quad_light()
+                         : what == "preset:cornell_box_mesh" ? pbrs::preset::cornell_box_mesh()
+                                                             : pbrs::scene_file::build_scene(what);
         pbrs_scene *s = sc.commit();
         pbrs_scene_info info;
         pbrs::check(pbrs_scene_get_info(s, &info), "get_info");

@@ -92,6 +92,21 @@ def test_cpp_scene_file_loader_equals_python_loader(tmp_path, hostsim_api, which
     assert (a[0] != 0xFFFFFFFF).mean() > 0.3
 
 
+@pytest.mark.parametrize("name,py", [("cornell_box", lambda: scenes.preset_cornell_box()), ("quad", lambda: scenes.preset_quad())])
+def test_cpp_presets_equal_python_presets(tmp_path, hostsim_api, name, py):
+    """scene/src/preset.rs written twice (include/pbrs_presets.hpp over the C++ constructors,
+    pbrs_b200/scenes.py over SceneDesc): same scene facts, bit-identical primary hits.  Covers the
+    ParallelQuad::new_* / Cuboid::from_points / with_transform mirrors of the C++ header."""
+    _build()
+    hdr, inst, prim, t = _cpp_ids("preset:" + name, tmp_path)
+    h = py().realize(hostsim_api)
+    info = h.info()
+    assert list(hdr[:7]) == [info.width, info.height, info.n_instances, info.n_meshes, info.n_spheres, info.n_triangles, info.n_lights]
+    a = h.render_ids(0, msaa=1, flags=4)
+    assert (inst == a[0]).all() and (prim == a[1]).all() and bits_equal(t, a[2]).all()
+    assert (a[0] != 0xFFFFFFFF).mean() > 0.1
+
+
 def test_cpp_loader_rejects_what_the_reference_cannot_load(tmp_path):
     _build()
     path = str(tmp_path / "bad.pbrt")

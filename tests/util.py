@@ -13,6 +13,11 @@ SMALL_SCENES = {
     "zoo_image": lambda: scenes.material_zoo(96, 72, env="image", delta_lights=True),
     "zoo_dusk": lambda: scenes.material_zoo(96, 72, env="dusk", delta_lights=False),
     "zoo_black": lambda: scenes.material_zoo(96, 72, env="black", delta_lights=True),
+    # the remaining Shapes of shape/src/simple.rs + IsoBlas<Sphere>
+    "shape_zoo": lambda: scenes.shape_zoo(96, 72),
+    "preset_cornell": lambda: scenes.preset_cornell_box(96, 96),
+    "preset_quad_light": lambda: scenes.preset_quad_light(96, 72),
+    "preset_everything": lambda: scenes.preset_everything(96, 72, n_balls=150, n_boxes=6),
 }
 
 def _edge_single():

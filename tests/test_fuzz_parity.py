@@ -1,6 +1,6 @@
 """Randomised scenes: triangle soups (incl. slivers, duplicates, axis-aligned and coplanar faces),
 spheres, instances under random affine transforms (non-uniform scale, shear), random lights and
-materials.  The product's walks and shading must agree with the oracle on every one of them --
+materials; a second family adds quads, cuboids, disks, a sphere BLAS and a quad or disk light.  The product's walks and shading must agree with the oracle on every one of them --
 this is what exercises the exact-order TLAS/BLAS emulation (extent quirks, tie-breaks, oversized
 leaves) far from the hand-made scenes.  CPU: host build of the stage functions; GPU: the kernels."""
 import numpy as np
@@ -12,7 +12,46 @@ from pbrs_b200.scenes import GOLD, SILVER
 from tests.util import assert_radiance_close, assert_stats_close, bits_equal
 
 
-def random_scene(seed, w=72, h=56):
+def _add_simple_shapes(sd, mats, seed):
+    """Quads, cuboids, disks and a sphere BLAS under random transforms, and a quad or disk light
+    (their own generator, so the base scenes of the plain seeds stay what they were)."""
+    rng = np.random.default_rng(seed + 99991)
+    shapes = []
+    for _ in range(int(rng.integers(1, 4))):
+        shapes.append(sd.add_quad(tuple(rng.uniform(-1.5, 1.5, 3)), tuple(rng.normal(size=3)), tuple(rng.normal(size=3))))
+    for _ in range(int(rng.integers(1, 3))):
+        shapes.append(sd.add_cuboid(tuple(rng.uniform(-1.5, 0.0, 3)), tuple(rng.uniform(0.0, 1.5, 3))))
+    for _ in range(int(rng.integers(1, 3))):
+        n = rng.normal(size=3)
+        r = np.cross(n, rng.normal(size=3))
+        r = r / np.linalg.norm(r) * rng.uniform(0.3, 1.2)
+        n32 = (n / np.linalg.norm(n)).astype(np.float32)
+        r32 = r.astype(np.float32)
+        if abs(float(np.dot(r32, n32 / np.linalg.norm(n32)))) < 5e-7:   # Disk::new asserts |radial . n| < 1e-6
+            shapes.append(sd.add_disk(tuple(rng.uniform(-1.5, 1.5, 3)), tuple(n32), tuple(r32)))
+    nb = int(rng.choice([1, 3, 4, 5, 17, 60]))
+    shapes.append(sd.add_sphere_blas(np.concatenate([rng.uniform(-1.2, 1.2, (nb, 3)), rng.uniform(0.05, 0.5, (nb, 1))], axis=1)))
+    for sh in shapes:
+        for _ in range(int(rng.integers(1, 3))):
+            if rng.random() < 0.3:
+                fwd = None
+            else:
+                fwd = np.eye(4)
+                fwd[:3, :3] = rng.normal(size=(3, 3)) * 0.3 + np.eye(3) * rng.uniform(0.6, 1.4)
+                fwd[:3, 3] = rng.uniform(-2.5, 2.5, 3)
+            sd.add_instance(sh, int(rng.choice(mats)), fwd=fwd)
+    L = tuple(rng.uniform(5, 25, 3))
+    if rng.random() < 0.5:
+        o, u, v = tuple(rng.uniform(-1, 1, 3) + np.array([0, 3.0, 0])), (float(rng.uniform(0.5, 2)), 0.0, 0.2), (0.1, 0.0, float(rng.uniform(0.5, 2)))
+        sd.add_instance(sd.add_quad(o, u, v), sd.diffuse_light(L))
+        sd.add_area_light_quad(o, u, v, L)
+    else:
+        c, n, r = tuple(rng.uniform(-1, 1, 3) + np.array([0, 3.0, 0])), (0.0, -1.0, 0.0), (float(rng.uniform(0.3, 1.0)), 0.0, 0.0)
+        sd.add_instance(sd.add_disk(c, n, r), sd.diffuse_light(L))
+        sd.add_area_light_disk(c, n, r, L)
+
+
+def random_scene(seed, w=72, h=56, ext=False):
     rng = np.random.default_rng(seed)
     sd = SceneDesc()
     eye = rng.uniform(-1.0, 1.0, 3) + np.array([0.0, 0.5, -7.0])
@@ -73,6 +112,8 @@ def random_scene(seed, w=72, h=56):
         sd.add_point_light(tuple(rng.uniform(-4, 4, 3)), tuple(rng.uniform(5, 40, 3)))
     if rng.random() < 0.4:
         sd.add_distant_light(tuple(rng.normal(size=3)), tuple(rng.uniform(0.2, 1.5, 3)))
+    if ext:
+        _add_simple_shapes(sd, mats, seed)
     env = rng.integers(0, 4)
     if env == 0:
         sd.set_env_constant(tuple(rng.uniform(0.0, 0.4, 3)))
@@ -81,8 +122,8 @@ def random_scene(seed, w=72, h=56):
     return sd
 
 
-def _check(oracle_api, api, seed, n_bad_allowed=2e-3):
-    sd = random_scene(seed)
+def _check(oracle_api, api, seed, n_bad_allowed=2e-3, ext=False):
+    sd = random_scene(seed, ext=ext)
     ho, hp = sd.realize(oracle_api), sd.realize(api)
     a, b = ho.render_ids(0, msaa=1), hp.render_ids(0, msaa=1)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bits_equal(a[2], b[2]).all(), f"seed {seed}: primary hits differ"
@@ -102,3 +143,14 @@ def test_random_scenes_hostsim(oracle_api, hostsim_api, seed):
 @pytest.mark.parametrize("seed", range(12))
 def test_random_scenes_gpu(oracle_api, gpu_api, seed):
     _check(oracle_api, gpu_api, 1000 + seed)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_scenes_with_simple_shapes_hostsim(oracle_api, hostsim_api, seed):
+    _check(oracle_api, hostsim_api, 2000 + seed, ext=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_with_simple_shapes_gpu(oracle_api, gpu_api, seed):
+    _check(oracle_api, gpu_api, 2000 + seed, ext=True)

@@ -5,8 +5,8 @@
 //           scene_parser/src/lexer.rs:41-56 (`Include`)
 //   parser  scene_parser/src/parser.rs (scene-wide options, WorldBegin..WorldEnd, attribute and
 //           transform blocks; a one-element bracket list is a Number, :230-239)
-//   loader  scene/src/loader.rs (camera :91-135; world items :164-305; sphere / trianglemesh
-//           :307-389; area lights on spheres :396-434; distant / point / infinite lights; the
+//   loader  scene/src/loader.rs (camera :91-135; world items :164-305; sphere / trianglemesh /
+//           plymesh :307-389 with scene/src/plyloader.rs; area lights on spheres and PLY meshes :396-434; distant / point / infinite lights; the
 //           materials glass / mirror / matte / metal / plastic / uber / substrate :483-714;
 //           `Rotate` with the negated angle :792-798; quirks Q16 of SURVEY.md)
 // Where the reference panics or hits unimplemented!() this throws pbrs::Error(PBRS_ERR_UNSUPPORTED).
@@ -101,6 +101,124 @@ inline void tokenize(const std::string &text, const std::string &root, std::vect
 }
 
 // scene_parser/src/ast.rs ArgValue / ParameterSet
+// ---------------------------------------------------------------------------------------------
+// PLY meshes: scene/src/plyloader.rs:69-256 (binary payloads, float vertex properties, polygons
+// fanned) + geometry/src/lib.rs:16-32 (compute_normals).  Upstream the file is cut off right after
+// the normals are computed; the tail here is what the signature and call sites require: uv
+// defaults to (0, 0) and the arrays become TriangleMeshRaw.  pbrt_loader.load_ply is the same code.
+// ---------------------------------------------------------------------------------------------
+struct PlyMesh {
+    std::vector<float> P, N, UV;
+    std::vector<uint32_t> idx;
+};
+inline std::vector<float> compute_normals(const std::vector<float> &P, const std::vector<uint32_t> &idx) {
+    std::vector<float> acc(P.size(), 0.0f);
+    for (size_t t = 0; t + 2 < idx.size(); t += 3) {
+        const float *p0 = &P[3 * idx[t]], *p1 = &P[3 * idx[t + 1]], *p2 = &P[3 * idx[t + 2]];
+        const float a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, b[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+        const float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        for (int v = 0; v < 3; ++v)
+            for (int c = 0; c < 3; ++c) acc[3 * idx[t + v] + c] += n[c];
+    }
+    for (size_t v = 0; v + 2 < acc.size(); v += 3) {
+        float n2 = (acc[v] * acc[v] + acc[v + 1] * acc[v + 1]) + acc[v + 2] * acc[v + 2];
+        if (!(n2 != 0.0f && std::isfinite(n2))) throw Error(PBRS_ERR_UNSUPPORTED, "compute_normals: a vertex has no (finite, non-zero) normal; Vec3::hat panics upstream");
+        float inv = 1.0f / std::sqrt(n2);
+        for (int c = 0; c < 3; ++c) acc[v + c] = acc[v + c] * inv;
+    }
+    return acc;
+}
+inline PlyMesh load_ply(const std::string &path) {
+    const std::string data = read_file(path);
+    size_t pos = 0;
+    auto line = [&]() {
+        size_t end = data.find('\n', pos);
+        if (end == std::string::npos) throw Error(PBRS_ERR_INVALID_ARG, "ply: unexpected end of header");
+        std::string out = data.substr(pos, end - pos);
+        pos = end + 1;
+        while (!out.empty() && (out.back() == '\r' || out.back() == ' ')) out.pop_back();
+        size_t b = out.find_first_not_of(' ');
+        return b == std::string::npos ? std::string() : out.substr(b);
+    };
+    auto split = [](const std::string &s) {
+        std::vector<std::string> w;
+        std::stringstream ss(s);
+        std::string part;
+        while (std::getline(ss, part, ' ')) w.push_back(part);
+        return w;
+    };
+    auto type_size = [](const std::string &n) { return (n == "uchar" || n == "uint8") ? 1 : n == "short" ? 2 : (n == "int" || n == "uint") ? 4 : 0; };  // :14-21
+    auto count = [](const std::string &n, long &out) {
+        if (n.empty() || n.find_first_not_of("0123456789") != std::string::npos) return false;
+        out = std::stol(n);
+        return true;
+    };
+    if (line() != "ply") throw Error(PBRS_ERR_INVALID_ARG, "ply: Header isn't ply");
+    std::vector<std::string> fw = split(line());
+    if (fw.size() < 2 || fw[0] != "format") throw Error(PBRS_ERR_INVALID_ARG, "ply: Format line is bad");
+    const std::string fmt = fw[1];
+    if (fmt != "ascii" && fmt != "binary_little_endian" && fmt != "binary_big_endian") throw Error(PBRS_ERR_INVALID_ARG, "ply: Unrecognized format string: " + fmt);
+    std::vector<std::string> props;
+    long nv = -1, nf = -1;
+    int len_size = 0, el_size = 0;
+    while (true) {
+        std::string ln = line();
+        if (ln == "end_header") break;
+        if (ln.rfind("comment", 0) == 0) continue;
+        std::vector<std::string> w = split(ln);
+        if (w.size() < 3) throw Error(PBRS_ERR_INVALID_ARG, "ply: Can't handle the line " + ln);
+        if (w.size() == 3 && w[0] == "element" && w[1] == "vertex") { if (!count(w[2], nv)) nv = -1; }
+        else if (w.size() == 3 && w[0] == "element" && w[1] == "face") { if (!count(w[2], nf)) nf = -1; }
+        else if (w.size() == 3 && w[0] == "property" && w[1] == "float") props.push_back(w[2]);
+        else if (w.size() == 5 && w[0] == "property" && w[1] == "list" && w[4] == "vertex_indices") { len_size = type_size(w[2]); el_size = type_size(w[3]); }
+        else if (w[0] == "property") throw unsupported("ply: unsupported property line '" + ln + "' (only float vertex properties and a vertex_indices list)");
+    }
+    if (nv < 0 || nf < 0 || !len_size || !el_size) throw Error(PBRS_ERR_INVALID_ARG, "ply: header lacks vertex / face counts or the vertex_indices list");
+    if (fmt == "ascii") throw unsupported("ply: ascii payloads are not supported (bytes_to_f32 panics upstream)");
+    const bool le = fmt == "binary_little_endian";
+    auto u_at = [&](size_t at, int size) {
+        uint32_t v = 0;
+        for (int b = 0; b < size; ++b) v |= uint32_t((unsigned char)data[at + (le ? b : size - 1 - b)]) << (8 * b);
+        return v;
+    };
+    const size_t stride = props.size();
+    if (pos + size_t(nv) * stride * 4 > data.size()) throw Error(PBRS_ERR_INVALID_ARG, "ply: vertex block is truncated");
+    std::vector<float> vb(size_t(nv) * stride);
+    for (size_t k = 0; k < vb.size(); ++k) { uint32_t u = u_at(pos + 4 * k, 4); std::memcpy(&vb[k], &u, 4); }
+    pos += vb.size() * 4;
+    PlyMesh m;
+    for (long f = 0; f < nf; ++f) {
+        if (pos + len_size > data.size()) throw Error(PBRS_ERR_INVALID_ARG, "ply: face block is truncated");
+        uint32_t n = u_at(pos, len_size);
+        pos += len_size;
+        if (pos + size_t(n) * el_size > data.size()) throw Error(PBRS_ERR_INVALID_ARG, "ply: face block is truncated");
+        if (n == 0) throw Error(PBRS_ERR_INVALID_ARG, "ply: empty face (list_length - 1 underflows upstream)");
+        std::vector<uint32_t> face(n);
+        for (uint32_t k = 0; k < n; ++k) face[k] = u_at(pos + size_t(k) * el_size, el_size);
+        pos += size_t(n) * el_size;
+        if (n == 3) m.idx.insert(m.idx.end(), {face[0], face[1], face[2]});
+        else for (uint32_t k = 1; k + 1 < n; ++k) m.idx.insert(m.idx.end(), {face[0], face[k], face[k + 1]});  // fan, :184-190
+    }
+    for (uint32_t v : m.idx) if (v >= uint32_t(nv)) throw Error(PBRS_ERR_INVALID_ARG, "ply: vertex index out of range");
+    int ox = -1, oy = -1, oz = -1, onx = -1, ony = -1, onz = -1, ou = -1, ov = -1;
+    for (size_t k = 0; k < stride; ++k) {
+        const std::string &n = props[k];
+        if (n == "x") ox = int(k); else if (n == "y") oy = int(k); else if (n == "z") oz = int(k);
+        else if (n == "nx") onx = int(k); else if (n == "ny") ony = int(k); else if (n == "nz") onz = int(k);
+        else if (n == "u") ou = int(k); else if (n == "v") ov = int(k);
+    }
+    if (ox < 0 || oy < 0 || oz < 0) throw Error(PBRS_ERR_INVALID_ARG, "ply: position xyz: some missing");
+    const bool has_n = onx >= 0 && ony >= 0 && onz >= 0, has_uv = ou >= 0 && ov >= 0;
+    for (long v = 0; v < nv; ++v) {
+        const float *row = &vb[size_t(v) * stride];
+        m.P.insert(m.P.end(), {row[ox], row[oy], row[oz]});
+        if (has_n) m.N.insert(m.N.end(), {row[onx], row[ony], row[onz]});
+        if (has_uv) { m.UV.push_back(row[ou]); m.UV.push_back(row[ov]); } else { m.UV.push_back(0.0f); m.UV.push_back(0.0f); }
+    }
+    if (!has_n) m.N = compute_normals(m.P, m.idx);
+    return m;
+}
+
 struct Arg {
     enum Kind { Number, Numbers, String } kind = Number;
     float number = 0.0f;
@@ -286,7 +404,15 @@ struct Loader {
             if (ps.extract_substr("normal", key, nrm)) normals = nrm.numbers;
             return shape::TriangleMesh::from_soa(P.numbers, normals, uvs, tri);
         }
-        throw unsupported("shape of " + impl + " (plymesh: truncated upstream; loopsubdiv: pre-process)");
+        if (impl == "plymesh") {  // :314-331
+            PlyMesh m = ply(ps);
+            return shape::TriangleMesh::from_soa(m.P, m.N, m.UV, m.idx);
+        }
+        throw unsupported("shape of " + impl + " (loopsubdiv: pre-process)");
+    }
+    PlyMesh ply(Params &ps) {
+        for (auto &p : ps.kv) if (p.first == "string filename" && p.second.kind == Arg::String) return load_ply(root + "/" + p.second.str);  // lookup_string
+        throw Error(PBRS_ERR_INVALID_ARG, "no ply file specified");
     }
 
     static void apply(const float m[4][4], const float v[4], float out[3]) {
@@ -301,7 +427,27 @@ struct Loader {
             Params ps = parameter_list();
             Arg a; ps.extract("alpha", a);
             const InstanceTransform &c = ctm.back();
-            if (has_area_l) {
+            if (has_area_l && impl == "plymesh") {
+                // parse_samplable_shape, :408-433: one IsolatedTriangle instance and one triangle light
+                // (world-space vertices) per face.  The instance is a one-triangle mesh with the index
+                // triple (0, 2, 1), which undoes TriangleMesh's (i, k, j) swap: same t, same position.
+                PlyMesh m = ply(ps);
+                MaterialRef light_mtl = mtl::DiffuseLight::create(area_l);
+                for (size_t f = 0; f + 2 < m.idx.size(); f += 3) {
+                    std::vector<float> tri;
+                    Point3 w[3];
+                    for (int v = 0; v < 3; ++v) {
+                        const float *pv = &m.P[3 * m.idx[f + v]];
+                        tri.insert(tri.end(), {pv[0], pv[1], pv[2]});
+                        const float hv[4] = {pv[0], pv[1], pv[2], 1.0f};
+                        float o[3];
+                        apply(c.fwd, hv, o);  // SamplableShape::transformed_by, light/src/sample_shape.rs:63-68
+                        w[v] = {o[0], o[1], o[2]};
+                    }
+                    area.emplace_back(area_l, light::SamplableShape::Triangle(w[0], w[1], w[2]));
+                    instances.push_back(Instance(shape::TriangleMesh::from_soa(tri, {}, {}, {0, 2, 1}), light_mtl).with_transform(c));
+                }
+            } else if (has_area_l) {
                 if (impl != "sphere") throw unsupported("samplable shape: " + impl);
                 float r = 1.0f; ps.lookup_f32("float radius", r);
                 // SamplableShape::transformed_by, light/src/sample_shape.rs:46-82

@@ -15,8 +15,9 @@ inverse Mat4 multiplied separately, geometry/src/transform.rs:185-194; `Rotate` 
 angle, loader.rs:792-798; Mat4 x Mat4 column by column, math/src/hcm.rs:546-556).
 
 Unsupported directives raise `PbrtError` where the reference panics / hits `unimplemented!()`
-(plymesh: scene/src/plyloader.rs does not compile upstream; loopsubdiv, fourier, spectrum / xyz /
-blackbody colours, ObjectBegin/ObjectInstance: out of scope).
+(plymesh: scene/src/plyloader.rs is cut off upstream; its tail is restated here, see load_ply.
+loopsubdiv, fourier, spectrum / xyz / blackbody colours, ObjectBegin/ObjectInstance: out of scope,
+DESIGN.md section 8).
 """
 import os
 import re
@@ -148,6 +149,147 @@ class Affine:
 
     def apply_vec(self, v):
         return _mat_vec(self.fwd, np.array([v[0], v[1], v[2], 0.0], F32))[:3]
+
+
+# ---------------------------------------------------------------------------------------------
+# PLY meshes: scene/src/plyloader.rs:69-256 (binary only; float vertex properties; polygons are
+# fanned) and geometry/src/lib.rs:16-32 (compute_normals).  The file is cut off upstream right
+# after the normals are computed; the tail restated here is what the signature and
+# the call sites (loader.rs:314-331,408-419) require: Vertex{pos, normal, uv} with uv defaulting
+# to (0, 0), then TriangleMeshRaw{vertices, index_triples}.
+# ---------------------------------------------------------------------------------------------
+_PLY_SIZES = {"uchar": 1, "uint8": 1, "short": 2, "int": 4, "uint": 4}  # get_type_size, :14-21
+
+
+def _cross32(a, b):  # hcm.rs:89-98, per row, in f32
+    return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                     a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], axis=1).astype(F32)
+
+
+def compute_normals(P, idx):
+    """geometry/src/lib.rs:16-32: face normals (p1-p0)x(p2-p0) accumulated per vertex in triangle
+    order (f32), then Vec3::hat.  A vertex no triangle touches makes hat() panic upstream."""
+    P = np.asarray(P, F32)
+    n = _cross32(P[idx[:, 1]] - P[idx[:, 0]], P[idx[:, 2]] - P[idx[:, 0]])
+    acc = np.zeros_like(P)
+    np.add.at(acc, idx.reshape(-1), np.repeat(n, 3, axis=0))  # unbuffered, in (i, j, k) order per triangle
+    n2 = ((acc[:, 0] * acc[:, 0] + acc[:, 1] * acc[:, 1]) + acc[:, 2] * acc[:, 2]).astype(F32)
+    if not (np.isfinite(n2) & (n2 != 0)).all():
+        raise PbrtError("compute_normals: a vertex has no (finite, non-zero) normal; Vec3::hat panics upstream")
+    inv = (F32(1.0) / np.sqrt(n2)).astype(F32)
+    return (acc * inv[:, None]).astype(F32)
+
+
+def load_ply(path):
+    """-> (P[n,3], N[n,3], UV[n,2], idx[m,3]) as the reference's TriangleMeshRaw would hold them."""
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = 0
+
+    def line():
+        nonlocal pos
+        end = data.find(b"\n", pos)
+        if end < 0:
+            raise PbrtError("ply: unexpected end of header")
+        out = data[pos:end + 1].decode("ascii", "replace")
+        pos = end + 1
+        return out
+
+    if line().strip() != "ply":
+        raise PbrtError("ply: Header isn't ply")
+    words = line().split(" ")
+    if words[0] != "format" or len(words) < 2:
+        raise PbrtError("ply: Format line is bad")
+    fmt = words[1].strip()
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+        raise PbrtError(f"ply: Unrecognized format string: {fmt}")
+    props, nv, nf, len_size, el_size = [], None, None, None, None
+    while True:
+        ln = line().strip()
+        if ln == "end_header":
+            break
+        if ln.startswith("comment"):
+            continue
+        w = ln.split(" ")
+        if len(w) < 3:
+            raise PbrtError(f"ply: Can't handle the line {ln}")
+        if w[:2] == ["element", "vertex"] and len(w) == 3:
+            nv = int(w[2]) if w[2].isdigit() else None
+        elif w[:2] == ["element", "face"] and len(w) == 3:
+            nf = int(w[2]) if w[2].isdigit() else None
+        elif w[:2] == ["property", "float"] and len(w) == 3:
+            props.append(w[2])
+        elif w[:2] == ["property", "list"] and len(w) == 5 and w[4] == "vertex_indices":
+            len_size, el_size = _PLY_SIZES.get(w[2]), _PLY_SIZES.get(w[3])
+        elif w[0] == "property":
+            # upstream only warns and then mis-reads the vertex block (its size assumes floats only)
+            raise PbrtError(f"ply: unsupported property line '{ln}' (only float vertex properties and a vertex_indices list)")
+        # other element kinds: "Unprocessed header line" upstream
+    if None in (nv, nf, len_size, el_size):
+        raise PbrtError("ply: header lacks vertex / face counts or the vertex_indices list")
+    if fmt == "ascii":
+        raise PbrtError("ply: ascii payloads are not supported (bytes_to_f32 panics upstream)")
+    e = "<" if fmt == "binary_little_endian" else ">"
+    stride = len(props)
+    nbytes = nv * stride * 4
+    if pos + nbytes > len(data):
+        raise PbrtError("ply: vertex block is truncated")
+    vb = np.frombuffer(data, dtype=e + "f4", count=nv * stride, offset=pos).astype(F32).reshape(nv, stride)
+    pos += nbytes
+    tris = []
+    for _ in range(nf):
+        if pos + len_size > len(data):
+            raise PbrtError("ply: face block is truncated")
+        n = int.from_bytes(data[pos:pos + len_size], "little" if e == "<" else "big")
+        pos += len_size
+        if pos + n * el_size > len(data):
+            raise PbrtError("ply: face block is truncated")
+        if n == 0:
+            raise PbrtError("ply: empty face (list_length - 1 underflows upstream)")
+        face = np.frombuffer(data, dtype=e + {1: "u1", 2: "u2", 4: "u4"}[el_size], count=n, offset=pos).astype(np.int64)
+        pos += n * el_size
+        if n == 3:
+            tris.append((face[0], face[1], face[2]))
+        else:  # fan, :184-190
+            for i in range(1, n - 1):
+                tris.append((face[0], face[i], face[i + 1]))
+    idx = np.array(tris, np.int64).reshape(-1, 3)
+    if idx.size and (idx.min() < 0 or idx.max() >= nv):
+        raise PbrtError("ply: vertex index out of range")
+    off = {name: i for i, name in enumerate(props)}  # the last occurrence wins, as in the match loop (:211-223)
+    if not all(k in off for k in ("x", "y", "z")):
+        raise PbrtError("ply: position xyz: some missing")
+    P = vb[:, [off["x"], off["y"], off["z"]]].copy()
+    idx = idx.astype(np.uint32)
+    if all(k in off for k in ("nx", "ny", "nz")):
+        N = vb[:, [off["nx"], off["ny"], off["nz"]]].copy()
+    else:
+        N = compute_normals(P, idx)
+    UV = vb[:, [off["u"], off["v"]]].copy() if ("u" in off and "v" in off) else np.zeros((nv, 2), F32)
+    return P, N, UV, idx
+
+
+def write_ply(path, P, idx, N=None, UV=None, big_endian=False, index_type="int", polygons=None):
+    """Binary PLY writer for fixtures (the subset load_ply reads).  `polygons`: optional list of
+    index lists written instead of `idx` (to exercise the fan triangulation)."""
+    P = np.asarray(P, F32)
+    cols, names = [P], ["x", "y", "z"]
+    if N is not None:
+        cols.append(np.asarray(N, F32)); names += ["nx", "ny", "nz"]
+    if UV is not None:
+        cols.append(np.asarray(UV, F32)); names += ["u", "v"]
+    faces = [list(map(int, t)) for t in (polygons if polygons is not None else np.asarray(idx).reshape(-1, 3))]
+    e = ">" if big_endian else "<"
+    it = {"uchar": "u1", "short": "u2", "int": "u4", "uint": "u4"}[index_type]
+    with open(path, "wb") as f:
+        hdr = ["ply", f"format binary_{'big' if big_endian else 'little'}_endian 1.0", "comment written by pbrs_b200",
+               f"element vertex {P.shape[0]}"] + [f"property float {n}" for n in names] + \
+              [f"element face {len(faces)}", f"property list uchar {index_type} vertex_indices", "end_header"]
+        f.write(("\n".join(hdr) + "\n").encode("ascii"))
+        f.write(np.concatenate(cols, axis=1).astype(e + "f4").tobytes())
+        for face in faces:
+            f.write(bytes([len(face)]))
+            f.write(np.asarray(face, e + it).tobytes())
 
 
 def _to_radians(deg):  # f32::to_radians
@@ -434,7 +576,16 @@ class Loader:
             nrm = ps.extract_substr("normal")
             N = np.zeros_like(P) if nrm is None else np.array(nrm[1], F32).reshape(-1, 3)
             return self.sd.add_mesh(P, idx, N=N, UV=UV)
-        raise PbrtError(f"shape of {impl} is out of scope (plymesh: truncated upstream; loopsubdiv: pre-process)")
+        if impl == "plymesh":  # :314-331
+            P, N, UV, idx = self.ply(ps)
+            return self.sd.add_mesh(P, idx, N=N, UV=UV)
+        raise PbrtError(f"shape of {impl} is out of scope (loopsubdiv: pre-process)")
+
+    def ply(self, ps):
+        name = ps.get("string filename")  # ParameterSet::lookup_string
+        if not isinstance(name, str):
+            raise PbrtError("no ply file specified")
+        return load_ply(os.path.join(self.root, name))
 
     @staticmethod
     def transform_of(t):  # :784-803
@@ -482,9 +633,21 @@ class Loader:
             _, impl, ps = item
             ps.extract("alpha")
             ctm = self.ctm[-1]
-            if self.area_l is not None:
+            if self.area_l is not None and impl == "plymesh":
+                # parse_samplable_shape, :408-433: one IsolatedTriangle instance + one triangle area
+                # light (world-space vertices) per face.  The instance is a one-triangle mesh whose
+                # index triple (0, 2, 1) undoes TriangleMesh's (i, k, j) swap, so t and the hit
+                # position are the IsolatedTriangle's bit for bit.
+                P, _, _, idx = self.ply(ps)
+                light_mtl = self.sd.diffuse_light(self.area_l)
+                for i, j, k in idx:
+                    tri = P[[i, j, k]]
+                    w = [tuple(float(c) for c in ctm.apply_point(v)) for v in tri]  # transformed_by, sample_shape.rs:63-68
+                    self.sd.add_area_light_triangle(w[0], w[1], w[2], self.area_l)
+                    self.instances.append((self.sd.add_mesh(tri, np.array([[0, 2, 1]], np.uint32)), light_mtl, ctm))
+            elif self.area_l is not None:
                 if impl != "sphere":
-                    raise PbrtError(f"samplable shape: {impl} (only sphere / plymesh upstream; plymesh is truncated)")
+                    raise PbrtError(f"samplable shape: {impl} is unimplemented!() upstream (only sphere / plymesh)")
                 r = ps.lookup_f32("float radius")
                 r = 1.0 if r is None else float(r)
                 # SamplableShape::transformed_by, light/src/sample_shape.rs:46-82

@@ -78,11 +78,15 @@ def _cpp_ids(path, tmp_path):
     return raw[:8], raw[8:8 + n].reshape(h, w), raw[8 + n:8 + 2 * n].reshape(h, w), raw[8 + 2 * n:8 + 3 * n].view(np.float32).reshape(h, w)
 
 
-@pytest.mark.parametrize("which", ["cornell", "mixed"])
+@pytest.mark.parametrize("which", ["cornell", "mixed", "ply"])
 def test_cpp_scene_file_loader_equals_python_loader(tmp_path, hostsim_api, which):
     _build()
     path = str(tmp_path / (which + ".pbrt"))
-    open(path, "w").write(scenes.cornell_box_pbrt(96, 72) if which == "cornell" else MIXED)
+    if which == "ply":   # plymesh shapes and PLY area lights, scene/src/plyloader.rs
+        from tests.test_scene_io import write_ply_scene
+        path = write_ply_scene(str(tmp_path))
+    else:
+        open(path, "w").write(scenes.cornell_box_pbrt(96, 72) if which == "cornell" else MIXED)
     hdr, inst, prim, t = _cpp_ids(path, tmp_path)
     h = load_pbrt(path).realize(hostsim_api)
     info = h.info()
@@ -111,9 +115,16 @@ def test_cpp_loader_rejects_what_the_reference_cannot_load(tmp_path):
     _build()
     path = str(tmp_path / "bad.pbrt")
     open(path, "w").write('Camera "perspective" Film "image" "integer xresolution" [ 8 ] "integer yresolution" [ 8 ] WorldBegin Material "matte" '
-                          'Shape "plymesh" "string filename" "x.ply" WorldEnd')
+                          'Shape "loopsubdiv" WorldEnd')
     r = subprocess.run([CHECK, path, str(tmp_path / "o.bin")], capture_output=True, text=True)
-    assert r.returncode == 5 and "plymesh" in r.stderr
+    assert r.returncode == 5 and "loopsubdiv" in r.stderr
+    # an ascii PLY: bytes_to_f32 panics upstream
+    open(str(tmp_path / "a.ply"), "w").write("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                                             "element face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    open(path, "w").write('Camera "perspective" Film "image" "integer xresolution" [ 8 ] "integer yresolution" [ 8 ] WorldBegin Material "matte" '
+                          'Shape "plymesh" "string filename" "a.ply" WorldEnd')
+    r = subprocess.run([CHECK, path, str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 5 and "ascii" in r.stderr
 
 
 def test_cpp_driver_has_no_cpu_fallback():

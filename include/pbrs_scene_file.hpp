@@ -333,7 +333,12 @@ struct Loader {
     static Color constant_color(const std::string &key, const std::vector<float> &n) {  // :758-766
         std::string type = key.substr(0, key.find(' '));
         if ((type == "rgb" || type == "color") && n.size() >= 3) return {n[0], n[1], n[2]};
-        throw unsupported("colour type '" + type + "' (xyz / blackbody / spectrum are load-time spectra: out of scope)");
+        if (type == "xyz" && n.size() >= 3) {  // Color::from_xyz, radiometry/src/color.rs:30-36
+            const float x = n[0], y = n[1], z = n[2];
+            return {3.240479f * x - 1.537150f * y - 0.498535f * z, -0.969256f * x + 1.875991f * y + 0.041556f * z,
+                    0.055648f * x - 0.204043f * y + 1.057311f * z};
+        }
+        throw unsupported("colour type '" + type + "' (blackbody / spectrum are load-time spectra over the CIE tables: out of scope)");
     }
     Color color_arg(Params &ps, const char *name, Color dflt) {
         std::string key; Arg a;

@@ -200,7 +200,12 @@ PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32
         f4 s = ld16(sc.spheres + index);
         sphere_intersect(mk(s.x, s.y, s.z), s.w, o, h, dg, f2u(tail.z) != 0u);
     } else if (kind != PBRS_SHAPE_MESH) {
-        if (!simple_intersect(sc.simples + index, kind, o, h, dg)) flag(dg, P_MISC);
+        if (!simple_intersect(sc.simples + index, kind, o, h, dg)) {
+            // cannot happen (same inputs as during the walk); keep the record defined anyway
+            flag(dg, P_MISC);
+            h = isect_new(o.o, 0.0f, 0.0f, 0.0f, -o.d, -o.d, dg);
+            h.tangent = mk(1.0f, 0.0f, 0.0f);
+        }
     } else {
         TriVerts tv = load_tri(sc.tris + tri);
         if (tv.flags & PBRS_TRI_SPHERE) {

@@ -36,6 +36,20 @@ __device__ __forceinline__ uint32_t warp_push(uint32_t *count, bool pred) {
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     return base + (uint32_t)__popc(m & ((1u << lane_id()) - 1u));
 }
+// two pushes whose atomics are in flight together (one L2 round trip instead of two)
+__device__ __forceinline__ void warp_push2(uint32_t *c1, bool p1, uint32_t *c2, bool p2, uint32_t &s1, uint32_t &s2) {
+    const unsigned m1 = __ballot_sync(0xFFFFFFFFu, p1), m2 = __ballot_sync(0xFFFFFFFFu, p2);
+    uint32_t b1 = 0u, b2 = 0u;
+    if (lane_id() == 0u) {
+        if (m1) b1 = atomicAdd(c1, (uint32_t)__popc(m1));
+        if (m2) b2 = atomicAdd(c2, (uint32_t)__popc(m2));
+    }
+    b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+    b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+    const unsigned below = (1u << lane_id()) - 1u;
+    s1 = b1 + (uint32_t)__popc(m1 & below);
+    s2 = b2 + (uint32_t)__popc(m2 & below);
+}
 __device__ __forceinline__ void warp_add_stat(unsigned long long *dst, uint32_t v) {
     uint32_t s = __reduce_add_sync(0xFFFFFFFFu, v);
     if (lane_id() == 0u && s != 0u) atomicAdd(dst, (unsigned long long)s);
@@ -203,9 +217,9 @@ __global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(De
             so = INTEGRATOR == PBRS_INTEGRATOR_PATH ? stage_shade_path<CLS>(sc, pb, fp, bp, j, bounce, dg)
                                                     : stage_shade_direct<CLS>(sc, pb, fp, bp, j, bounce, dg);
         }
-        uint32_t s1 = warp_push(next_count, so.next);
+        uint32_t s1, s2;
+        warp_push2(next_count, so.next, shadow_count, so.shadow_rays > 0, s1, s2);
         if (so.next) next_queue[s1] = j;
-        uint32_t s2 = warp_push(shadow_count, so.shadow_rays > 0);
         if (so.shadow_rays > 0) pb.shadow_queue[s2] = j;
         rays += (uint32_t)so.shadow_rays;
     }

@@ -471,7 +471,12 @@ class Loader:
     def constant_color(spectrum_type, nums):  # :758-766
         if spectrum_type in ("rgb", "color"):
             return (float(nums[0]), float(nums[1]), float(nums[2]))
-        raise PbrtError(f"colour type {spectrum_type!r} is out of scope (xyz / blackbody / spectrum: load-time spectra)")
+        if spectrum_type == "xyz":  # Color::from_xyz, radiometry/src/color.rs:30-36 (f32, left to right)
+            x, y, z = F32(nums[0]), F32(nums[1]), F32(nums[2])
+            return (float(F32(3.240479) * x - F32(1.537150) * y - F32(0.498535) * z),
+                    float(F32(-0.969256) * x + F32(1.875991) * y + F32(0.041556) * z),
+                    float(F32(0.055648) * x - F32(0.204043) * y + F32(1.057311) * z))
+        raise PbrtError(f"colour type {spectrum_type!r} is out of scope (blackbody / spectrum: load-time spectra over the CIE tables)")
 
     def color_arg(self, ps, name, default):
         hit = ps.extract_substr(name)

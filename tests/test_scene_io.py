@@ -50,6 +50,16 @@ def test_parameter_lists_and_defaults():
     assert [s[1] for s in spheres] == [1.0, 3.0, 1.0]
 
 
+def test_xyz_colours_go_through_from_xyz():
+    # parse_constant_color "xyz" -> Color::from_xyz (radiometry/src/color.rs:30-36); D65 white -> ~(1,1,1)
+    c = pbrt_loader.Loader.constant_color("xyz", [0.95047, 1.0, 1.08883])
+    np.testing.assert_allclose(c, (1.0, 1.0, 1.0), atol=2e-4)
+    c = pbrt_loader.Loader.constant_color("xyz", [1.0, 0.0, 0.0])
+    np.testing.assert_allclose(c, (3.240479, -0.969256, 0.055648), rtol=1e-6)
+    with pytest.raises(PbrtError):
+        pbrt_loader.Loader.constant_color("blackbody", [6500.0, 1.0])
+
+
 def test_attribute_blocks_reset_material_and_scope_transforms():
     text = ('Camera "perspective" Film "image" "integer xresolution" [ 16 ] "integer yresolution" [ 8 ] WorldBegin '
             'Material "matte" AttributeBegin Shape "sphere" AttributeEnd '          # material reset inside the block: dropped

@@ -94,11 +94,19 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 #ifndef PBRS_REFILL_IDLE_LANES
 #define PBRS_REFILL_IDLE_LANES 20
 #endif
-constexpr int kRefillIdleLanes = PBRS_REFILL_IDLE_LANES;  // refill as soon as this many lanes are idle
+#ifndef PBRS_REFILL_IDLE_LANES_ANY
+#define PBRS_REFILL_IDLE_LANES_ANY PBRS_REFILL_IDLE_LANES
+#endif
+// refill as soon as this many lanes are idle (closest-hit / any-hit walks tuned separately)
+template <bool ANY> constexpr int kRefillIdleLanes = ANY ? PBRS_REFILL_IDLE_LANES_ANY : PBRS_REFILL_IDLE_LANES;
 #ifndef PBRS_LEAF_VOTE
 #define PBRS_LEAF_VOTE 8
 #endif
-constexpr int kLeafVote = PBRS_LEAF_VOTE;  // leave phase 1 once this many lanes wait at a leaf (32: all of them)
+#ifndef PBRS_LEAF_VOTE_ANY
+#define PBRS_LEAF_VOTE_ANY 12  // any-hit leaves are cheap to wait for: C5 shadow -7 %, C3/C4 unchanged (profiles/r1_exp_anyhit_vote.log)
+#endif
+// leave phase 1 once this many lanes wait at a leaf (32: all of them)
+template <bool ANY> constexpr int kLeafVote = ANY ? PBRS_LEAF_VOTE_ANY : PBRS_LEAF_VOTE;
 
 // `cnt` = this stage's counter block (PBRS_CNT_*).
 #ifndef PBRS_TRACE_BLOCKS_PER_SM
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
     while (true) {
         // ---- refill idle lanes ----
         unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
-        if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= kRefillIdleLanes)) {
+        if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= kRefillIdleLanes<ANY>)) {
             int leader = __ffs(idle) - 1;
             uint32_t base = 0u;
             if ((int)lane_id() == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
@@ -147,14 +155,14 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
             break;
         }
         // ---- phase 1: expansions / unwinds until every busy lane stands at a leaf or is done ----
-        if (kLeafVote >= 32) {
+        if (kLeafVote<ANY> >= 32) {
             while (busy && w.advancing()) w.advance(sc, dg, tc);
         } else {
             while (true) {
                 const bool adv = busy && w.advancing();
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, adv);
                 const unsigned waiting = __ballot_sync(0xFFFFFFFFu, busy && w.at_leaf());
-                if (m == 0u || __popc(waiting) >= kLeafVote) break;
+                if (m == 0u || __popc(waiting) >= kLeafVote<ANY>) break;
                 if (adv) w.advance(sc, dg, tc);
             }
         }

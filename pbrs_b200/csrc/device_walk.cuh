@@ -252,7 +252,7 @@ struct Walk {
 
     // ---- phase 2a: a leaf ----
     PB_DEV void leaf(const DeviceScene &sc, Diag &dg, TravCount &tc) {
-        const uint32_t first = next & ~PBRS_LEAF_BIT;
+        const uint32_t first = next & PBRS_LEAF_FIRST_MASK;
         next = PBRS_NONE;
         if (lvl) {
             // a run of triangles (shape/src/blas.rs:447-454): all see the extent of the pop

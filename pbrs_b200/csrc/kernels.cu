@@ -112,6 +112,9 @@ template <bool ANY> constexpr int kLeafVote = ANY ? PBRS_LEAF_VOTE_ANY : PBRS_LE
 #ifndef PBRS_TRACE_BLOCKS_PER_SM
 #define PBRS_TRACE_BLOCKS_PER_SM 8
 #endif
+#ifndef PBRS_COOP_ANY
+#define PBRS_COOP_ANY 1
+#endif
 template <bool ANY, bool COUNT, bool EXT>
 __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
     const uint32_t *count = cnt + (ANY ? PBRS_CNT_SHADOW : PBRS_CNT_EXTEND);
@@ -167,6 +170,58 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
             }
         }
         __syncwarp();
+#if PBRS_COOP_ANY
+        // ---- phase 2, any-hit: the triangle runs of all lanes at a BLAS leaf, spread over the warp ----
+        // A lane at a leaf has 1..6 triangles to test against its ray and typically 5-6 of the 32
+        // lanes are there, so testing them lane by lane, triangle after triangle, issues the test
+        // code ~3 times for ~6 lanes.  Here every (lane, triangle) pair gets a lane of its own:
+        // the owner's ray comes over by shuffle, the result goes back as a ballot.  Any-hit only:
+        // the outcome is an OR, no order to preserve.  (COUNT kernels keep the sequential walk,
+        // whose counters stop at the first occluder like the reference's.)
+        if (ANY && !COUNT && sc.has_mesh) {
+            __shared__ uint8_t coop_slots[kThreads];
+            uint8_t *slot = coop_slots + (threadIdx.x & ~31u);
+            bool mine = busy && w.at_leaf() && w.lvl != 0u && ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) != 0u;
+            unsigned owners = __ballot_sync(0xFFFFFFFFu, mine);
+            while (owners) {
+                const uint32_t c = mine ? ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) : 0u;
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if ((int)lane_id() >= d) incl += v;
+                }
+                const uint32_t excl = incl - c;
+                const bool in_pass = mine && incl <= 32u;  // the first owner always fits (c <= 6)
+                if (in_pass)
+                    for (uint32_t k = 0; k < c; ++k) slot[excl + k] = (uint8_t)(lane_id() | (k << 5));
+                const uint32_t total = __reduce_max_sync(0xFFFFFFFFu, in_pass ? incl : 0u);
+                __syncwarp();
+                const bool work = lane_id() < total;
+                const uint32_t e = work ? slot[lane_id()] : 0u;
+                const int src = (int)(e & 31u);
+                Ray r;
+                r.o.x = __shfl_sync(0xFFFFFFFFu, w.o.x, src); r.o.y = __shfl_sync(0xFFFFFFFFu, w.o.y, src); r.o.z = __shfl_sync(0xFFFFFFFFu, w.o.z, src);
+                r.d.x = __shfl_sync(0xFFFFFFFFu, w.d.x, src); r.d.y = __shfl_sync(0xFFFFFFFFu, w.d.y, src); r.d.z = __shfl_sync(0xFFFFFFFFu, w.d.z, src);
+                r.t_max = __shfl_sync(0xFFFFFFFFu, w.t_max, src);
+                const uint32_t first = __shfl_sync(0xFFFFFFFFu, w.tri_base + (w.next & PBRS_LEAF_FIRST_MASK), src);
+                bool hit = false;
+                if (work) {
+                    const TriVerts tv = load_tri(sc.tris + first + (e >> 5));
+                    if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { float t; hit = ball_test(tv.p0, tv.p1.x, r, true, t); }
+                    else hit = tri_occludes(tv.p0, tv.p1, tv.p2, r, dg);
+                }
+                const unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
+                if (in_pass) {
+                    if (hits & (((1u << c) - 1u) << excl)) { w.occluded = true; w.done = true; }
+                    w.next = PBRS_NONE;  // the leaf is consumed; phase 1 unwinds from here
+                    mine = false;
+                }
+                __syncwarp();
+                owners = __ballot_sync(0xFFFFFFFFu, mine);
+            }
+        }
+#endif
         // ---- phase 2: one leaf ----
         if (busy && w.at_leaf()) w.leaf(sc, dg, tc);
         if (ANY) {

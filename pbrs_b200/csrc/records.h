@@ -31,6 +31,13 @@ static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
 #define PBRS_NODE_LEFT_LEAF 4u
 #define PBRS_NODE_RIGHT_LEAF 8u
 #define PBRS_MAX_LEAF_PRIMS 16383u
+// A BLAS leaf link also carries the run length when it is short: bits 28..30 of child[k] hold the
+// number of primitives (1..6; 0 = longer, walk the run by its PBRS_TRI_LAST_IN_LEAF flag), bits
+// 0..27 the first primitive.  The any-hit kernel uses it to spread the triangle tests of all the
+// lanes that stand at a leaf over the whole warp.
+#define PBRS_LEAF_FIRST_MASK 0x0FFFFFFFu
+#define PBRS_LEAF_COUNT_SHIFT 28
+#define PBRS_LEAF_COUNT_MAX 6u
 
 // p0/p1/p2 already carry the reference's (i, k, j) vertex swap (shape/src/blas.rs:162-163):
 // p0 = pos[idx.0], p1 = pos[idx.2], p2 = pos[idx.1].
@@ -205,6 +212,7 @@ struct DeviceScene {
     float tlas_min[3], tlas_max[3];
     uint32_t tlas_root_is_leaf;  // a single instance
     uint32_t n_instances;
+    uint32_t has_mesh; // any BLAS at all (a scene of spheres skips the cooperative leaf phase)
     uint32_t has_ext;  // any quad / cuboid / disk instance or sphere BLAS: selects the EXT traversal kernels
 };
 

@@ -102,7 +102,8 @@ struct BlasBuilder {
         HostBox b = box_empty();
         for (size_t i = s; i < e; ++i) b = box_merge(b, tbox[perm[i]]);  // .sum::<BBox>()
         if (e > s) leaf_last.push_back((uint32_t)(e - 1));
-        return ChildLink{true, (uint32_t)s, (uint32_t)std::min<size_t>(e - s, PBRS_MAX_LEAF_PRIMS), b};
+        const uint32_t run = (e - s) <= PBRS_LEAF_COUNT_MAX ? (uint32_t)(e - s) : 0u;  // short runs carry their length
+        return ChildLink{true, (uint32_t)s | (run << PBRS_LEAF_COUNT_SHIFT), (uint32_t)std::min<size_t>(e - s, PBRS_MAX_LEAF_PRIMS), b};
     }
 
     ChildLink build(size_t s, size_t e, uint32_t depth = 1) {
@@ -468,6 +469,7 @@ int host_build(SceneImpl &s) {
             box_grow_point(b, pk);
             boxes[t] = b;
         }
+        if (nt > PBRS_LEAF_FIRST_MASK) { set_error("commit: a mesh has more primitives than a leaf link can address (2^28)"); return PBRS_ERR_UNSUPPORTED; }
         BlasBuilder bb(boxes);
         ChildLink root = bb.build(0, nt);
         if (bb.max_depth > 60) { set_error("commit: a BLAS is deeper than 60 levels (traversal stack)"); return PBRS_ERR_UNSUPPORTED; }
@@ -494,6 +496,7 @@ int host_build(SceneImpl &s) {
         in.box = transform_box(in.fwd, sb);
     }
     // ---- TLAS ----
+    if (s.instances.size() > PBRS_LEAF_FIRST_MASK) { set_error("commit: more instances than a leaf link can address (2^28)"); return PBRS_ERR_UNSUPPORTED; }
     TlasBuilder tb{s.instances, {}, 0};
     std::vector<uint32_t> all(s.instances.size());
     std::iota(all.begin(), all.end(), 0u);
@@ -637,6 +640,7 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     for (int k = 0; k < 3; ++k) { ds.tlas_min[k] = s.tlas_box.mn[k]; ds.tlas_max[k] = s.tlas_box.mx[k]; }
     ds.tlas_root_is_leaf = s.tlas_root_is_leaf ? 1u : 0u;
     ds.n_instances = (uint32_t)s.instances.size();
+    ds.has_mesh = s.meshes.empty() ? 0u : 1u;
     ds.has_ext = s.simples.empty() ? 0u : 1u;
     for (const HostMesh &m : s.meshes)
         if (!m.balls.empty()) ds.has_ext = 1u;

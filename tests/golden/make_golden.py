@@ -13,14 +13,14 @@ sys.path.insert(0, ROOT)
 from oracle import oracle_ffi  # noqa: E402
 from tests.util import SMALL_SCENES  # noqa: E402
 
-GOLDEN_SCENES = ["cornell", "spheres", "terrain", "field", "zoo_image"]
+GOLDEN_SCENES = ["cornell", "spheres", "terrain", "field", "zoo_image", "shape_zoo", "preset_cornell"]
 CROP = (16, 12, 48, 36)  # x, y, w, h
 
 
-def main():
+def main(only=None):
     api = oracle_ffi.load()
     out = os.path.dirname(os.path.abspath(__file__))
-    for name in GOLDEN_SCENES:
+    for name in (only or GOLDEN_SCENES):
         h = SMALL_SCENES[name]().realize(api)
         inst, prim, t = h.render_ids(0, msaa=2, crop=CROP)
         d1, _ = h.render_samples(integrator="path", msaa=2, max_depth=1, crop=CROP)
@@ -31,4 +31,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])  # optional scene names: regenerate only those

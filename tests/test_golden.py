@@ -9,7 +9,7 @@ import pytest
 from tests.util import SMALL_SCENES, assert_radiance_close, bits_equal
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["cornell", "spheres", "terrain", "field", "zoo_image"]
+NAMES = ["cornell", "spheres", "terrain", "field", "zoo_image", "shape_zoo", "preset_cornell"]
 
 
 def _check(api, name, exact):

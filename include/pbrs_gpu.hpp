@@ -80,6 +80,7 @@ class Camera {
 public:
     Camera(std::pair<uint32_t, uint32_t> resolution, Angle fov_y) : w_(resolution.first), h_(resolution.second), fov_(fov_y) {}
     Camera &look_at(Point3 from, Point3 target, Vec3 up) { eye_ = from; target_ = target; up_ = up; return *this; }
+    Camera looking_at(Point3 from, Point3 target, Vec3 up) const { Camera c = *this; c.look_at(from, target, up); return c; }  // camera.rs:46-56
     std::pair<uint32_t, uint32_t> resolution() const { return {w_, h_}; }
 private:
     friend class Scene;

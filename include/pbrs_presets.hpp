@@ -66,6 +66,51 @@ inline Scene quad_light() {
                           light::DiffuseAreaLight(light_power, light::SamplableShape::Sphere({0, 7, 0}, 2))});
 }
 
+// preset::two_perlin_spheres, scene/src/preset.rs:115-133
+inline Scene two_perlin_spheres() {
+    Camera camera({800, 800}, Angle::new_deg(20.0f));
+    camera.look_at(point3(13, 2, -3), point3(0, 0, 0), Vec3::Y());
+    MaterialRef mtl = mtl::Lambertian::textured(tex::Perlin::with_freq(4.0f));
+    std::vector<Instance> inst = {Instance(shape::Sphere::from_raw(0, -1000, 0, 1000), mtl), Instance(shape::Sphere::from_raw(0, 2, 0, 2), mtl)};
+    return Scene(std::move(inst), camera).with_fn_env_light(light::EnvFn::BlueSky);
+}
+
+// preset::plates, scene/src/preset.rs:259-358: four glossy plates tilted to mirror four sphere lights
+// of decreasing size into the camera (the classic MIS test scene)
+inline Scene plates() {
+    const float r = 20.0f;
+    auto hat = [](Vec3 v) { float inv = 1.0f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z); return Vec3{v.x * inv, v.y * inv, v.z * inv}; };
+    MaterialRef matte = mtl::Lambertian::solid(Color::gray(0.4f));
+    std::vector<Instance> inst = {Instance(shape::ParallelQuad::new_xy({-r, r}, {0.0f, r}, 0.0f), matte),
+                                  Instance(shape::ParallelQuad::new_xz({-r, r}, 0.0f, {-r, 0.0f}), matte)};
+    const Point3 lights_pos = point3(0.0f, r, -0.4f * r), camera_pos = point3(0.0f, 0.4f * r, -2.8f * r);
+    const float left = -r * 0.7f, right = r * 0.7f, plate_width = 0.16f * r;
+    const float pos_yz[4][2] = {{0.6f * r, -0.2f * r}, {0.45f * r, -0.3f * r}, {0.3f * r, -0.45f * r}, {0.2f * r, -0.6f * r}};
+    const float rough[4] = {8e-5f, 3e-4f, 8e-4f, 3e-3f};
+    for (int k = 0; k < 4; ++k) {
+        const float py = pos_yz[k][0], pz = pos_yz[k][1];
+        const Vec3 pl = hat({0.0f, lights_pos.y - py, lights_pos.z - pz}), pc = hat({0.0f, camera_pos.y - py, camera_pos.z - pz});
+        const Vec3 normal = hat({pl.x + pc.x, pl.y + pc.y, pl.z + pc.z});
+        Vec3 tangent = hat({0.0f, normal.z, -normal.y});
+        const float hw = plate_width * 0.5f;
+        tangent = {tangent.x * hw, tangent.y * hw, tangent.z * hw};
+        const Vec3 t00{left + tangent.x, py + tangent.y, pz + tangent.z}, t01{t00.x - tangent.x * 2.0f, t00.y - tangent.y * 2.0f, t00.z - tangent.z * 2.0f};
+        const Vec3 t10{right + tangent.x, py + tangent.y, pz + tangent.z}, t11{t10.x - tangent.x * 2.0f, t10.y - tangent.y * 2.0f, t10.z - tangent.z * 2.0f};
+        std::vector<float> P = {t00.x, t00.y, t00.z, t01.x, t01.y, t01.z, t10.x, t10.y, t10.z, t11.x, t11.y, t11.z}, N;
+        for (int v = 0; v < 4; ++v) N.insert(N.end(), {normal.x, normal.y, normal.z});
+        inst.emplace_back(shape::TriangleMesh::from_soa(P, N, {0, 0, 0, 1, 1, 0, 1, 1}, {0, 1, 2, 2, 1, 3}), mtl::Glossy::create(Color::gray(0.9f), rough[k]));
+    }
+    const float a = left * 0.9f, b = right * 0.9f, spacing = (b - a) * (1.0f / 4.0f);  // float::linspace, math/src/float.rs:140-155
+    const float sizes[4] = {0.1f * r, 0.06f * r, 0.03f * r, 0.01f * r};
+    const Color colors[4] = {{1.0f, 0.8f, 0.8f}, {1.0f, 1.0f, 0.8f}, {0.8f, 1.0f, 0.8f}, {0.8f, 0.8f, 1.0f}};
+    std::vector<light::DiffuseAreaLight> area;
+    for (int i = 0; i < 4; ++i) area.emplace_back(colors[i], light::SamplableShape::Sphere({spacing * (float(i) + 0.5f) + a, lights_pos.y, lights_pos.z}, sizes[i]));
+    for (int i = 0; i < 4; ++i) inst.emplace_back(shape::Sphere::create({spacing * (float(i) + 0.5f) + a, lights_pos.y, lights_pos.z}, sizes[i]), mtl::DiffuseLight::create(colors[i]));
+    Camera camera = Camera({1000, 800}, Angle::new_rad(3.14159265358979323846f * 0.19f))
+                        .looking_at(camera_pos, point3(camera_pos.x, camera_pos.y, camera_pos.z + 1.0f), Vec3::Y());
+    return Scene(std::move(inst), camera).with_lights({}, std::move(area));
+}
+
 // The C1 workload of bench.py: the same box with triangle walls and a sphere light (what the
 // loader can express, scene/src/loader.rs:396-434).
 inline Scene cornell_box_mesh() {

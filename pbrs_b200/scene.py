@@ -35,9 +35,9 @@ class SceneDesc:
         self.width = self.height = 0
 
     # -- camera (geometry/src/camera.rs:19-44) --
-    def set_camera(self, width, height, fov_y_deg, eye, target, up=(0.0, 1.0, 0.0)):
-        # f32::to_radians: deg * (PI / 180) evaluated in f32
-        fov = np.float32(fov_y_deg) * (np.float32(np.pi) / np.float32(180.0))
+    def set_camera(self, width, height, fov_y_deg, eye, target, up=(0.0, 1.0, 0.0), fov_y_rad=None):
+        # f32::to_radians: deg * (PI / 180) evaluated in f32 (fov_y_rad: an Angle already in radians)
+        fov = np.float32(fov_y_deg) * (np.float32(np.pi) / np.float32(180.0)) if fov_y_rad is None else np.float32(fov_y_rad)
         self.width, self.height = int(width), int(height)
         self.ops.append(("scene_set_camera", (int(width), int(height), float(fov), eye, target, up)))
 

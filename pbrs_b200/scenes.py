@@ -205,6 +205,49 @@ def preset_everything(width=800, height=800, n_balls=1000, n_boxes=20, seed=SEED
     return sd
 
 
+def preset_plates(width=1000, height=800):
+    """scene/src/preset.rs:259-358: a wall and a floor quad, four glossy plates (two-triangle
+    meshes tilted to mirror the lights into the camera, roughness 8e-5 .. 3e-3) and four sphere
+    lights of decreasing size.  Vertex arithmetic in f32 like the reference's."""
+    f = np.float32
+    r = f(20.0)
+    sd = SceneDesc()
+    cam = np.array([0.0, f(0.4) * r, f(-2.8) * r], f)
+    sd.set_camera(width, height, None, tuple(cam), tuple(cam + np.array([0, 0, 1], f)), (0, 1, 0),
+                  fov_y_rad=f(np.pi) * f(0.19))  # Angle::pi() * 0.19
+    matte = sd.lambertian((0.4, 0.4, 0.4))
+    sd.add_instance(sd.add_quad_xy((-r, r), (0.0, r), 0.0), matte)
+    sd.add_instance(sd.add_quad_xz((-r, r), 0.0, (-r, 0.0)), matte)
+    lights_pos = np.array([0.0, r, f(-0.4) * r], f)
+    left, right = -r * f(0.7), r * f(0.7)
+    hat = lambda v: (v * (f(1.0) / np.sqrt(f(f(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])))).astype(f)
+    plate_width = f(0.16) * r
+    for (ky, kz), rough in zip([(0.6, -0.2), (0.45, -0.3), (0.3, -0.45), (0.2, -0.6)], [8e-5, 3e-4, 8e-4, 3e-3]):
+        py, pz = f(ky) * r, f(kz) * r
+        pl = np.array([0.0, lights_pos[1] - py, lights_pos[2] - pz], f)
+        pc = np.array([0.0, cam[1] - py, cam[2] - pz], f)
+        normal = hat(hat(pl) + hat(pc))
+        tangent = hat(np.array([0.0, normal[2], -normal[1]], f)) * (plate_width * f(0.5))
+        t00 = np.array([left, py, pz], f) + tangent
+        t01 = t00 - tangent * f(2.0)
+        t10 = np.array([right, py, pz], f) + tangent
+        t11 = t10 - tangent * f(2.0)
+        P = np.stack([t00, t01, t10, t11]).astype(f)
+        mesh = sd.add_mesh(P, np.array([[0, 1, 2], [2, 1, 3]], np.uint32), N=np.tile(normal, (4, 1)),
+                           UV=np.array([[0, 0], [0, 1], [1, 0], [1, 1]], f))
+        sd.add_instance(mesh, sd.glossy((0.9, 0.9, 0.9), rough))
+    a, b = left * f(0.9), right * f(0.9)
+    spacing = (b - a) * f(1.0 / 4)                       # float::linspace, math/src/float.rs:140-155
+    sizes = [f(0.1) * r, f(0.06) * r, f(0.03) * r, f(0.01) * r]
+    colors = [(1.0, 0.8, 0.8), (1.0, 1.0, 0.8), (0.8, 1.0, 0.8), (0.8, 0.8, 1.0)]
+    spheres = [((float(spacing * f(i + 0.5) + a), float(lights_pos[1]), float(lights_pos[2])), float(sizes[i])) for i in range(4)]
+    for (c, rad), col in zip(spheres, colors):
+        sd.add_area_light_sphere(c, rad, col)
+    for (c, rad), col in zip(spheres, colors):
+        sd.add_instance(sd.add_sphere(c, rad), sd.diffuse_light(col))
+    return sd
+
+
 def shape_zoo(width=128, height=96, seed=SEED):
     """Every Shape of shape/src/simple.rs and both BLAS kinds in one small scene, plus a disk and a
     quad area light: the parity fixture of the simple-shape code."""

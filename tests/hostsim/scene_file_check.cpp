@@ -18,6 +18,7 @@ int main(int argc, char **argv) {
         pbrs::Scene sc = what == "preset:cornell_box" ? pbrs::preset::cornell_box()
                          : what == "preset:quad" ? pbrs::preset::quad_scene()
                          : what == "preset:quad_light" ? pbrs::preset::quad_light()
+                         : what == "preset:plates" ? pbrs::preset::plates()
                          : what == "preset:cornell_box_mesh" ? pbrs::preset::cornell_box_mesh()
                                                              : pbrs::scene_file::build_scene(what);
         pbrs_scene *s = sc.commit();

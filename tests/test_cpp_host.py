@@ -96,7 +96,8 @@ def test_cpp_scene_file_loader_equals_python_loader(tmp_path, hostsim_api, which
     assert (a[0] != 0xFFFFFFFF).mean() > 0.3
 
 
-@pytest.mark.parametrize("name,py", [("cornell_box", lambda: scenes.preset_cornell_box()), ("quad", lambda: scenes.preset_quad())])
+@pytest.mark.parametrize("name,py", [("cornell_box", lambda: scenes.preset_cornell_box()), ("quad", lambda: scenes.preset_quad()),
+                                     ("plates", lambda: scenes.preset_plates())])
 def test_cpp_presets_equal_python_presets(tmp_path, hostsim_api, name, py):
     """scene/src/preset.rs written twice (include/pbrs_presets.hpp over the C++ constructors,
     pbrs_b200/scenes.py over SceneDesc): same scene facts, bit-identical primary hits.  Covers the

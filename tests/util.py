@@ -18,6 +18,7 @@ SMALL_SCENES = {
     "preset_cornell": lambda: scenes.preset_cornell_box(96, 96),
     "preset_quad_light": lambda: scenes.preset_quad_light(96, 72),
     "preset_everything": lambda: scenes.preset_everything(96, 72, n_balls=150, n_boxes=6),
+    "preset_plates": lambda: scenes.preset_plates(100, 80),
 }
 
 def _edge_single():

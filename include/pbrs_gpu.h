@@ -116,6 +116,10 @@ int pbrs_scene_add_cuboid(pbrs_scene *, const float p0[3], const float p1[3]);
  * asserts).  intersect :306-326, occludes :328-332 (ignores the ray extent).  -> shape id */
 int pbrs_scene_add_disk(pbrs_scene *, const float center[3], const float normal[3],
                         const float radial[3]);
+/* IsolatedTriangle::new (shape/src/simple.rs:184-195; intersect :425-427 = intersect_triangle with
+ * dpdu = p1 - p0 and (u, v) = the barycentrics, occludes :428-430): the Shape the loader instances
+ * once per face of a PLY area light (scene/src/loader.rs:408-433).  -> shape id */
+int pbrs_scene_add_triangle(pbrs_scene *, const float p0[3], const float p1[3], const float p2[3]);
 /* IsoBlas::<Sphere>::build (shape/src/blas.rs:60-69, traversal :263-275): n spheres as
  * (cx, cy, cz, radius) under one bottom-level BVH.  The primitive id reported for a hit is the
  * sphere's index in this array.  -> shape id */

@@ -272,10 +272,10 @@ struct Substrate {
 
 // ---- shapes (shape/src/simple.rs, shape/src/blas.rs) ----------------------------------------
 struct Shape {
-    enum Kind { SphereK, MeshK, QuadK, CuboidK, DiskK, SphereBlasK } kind = SphereK;
-    Point3 center;                 // sphere / disk centre, quad origin, cuboid corner 0
+    enum Kind { SphereK, MeshK, QuadK, CuboidK, DiskK, SphereBlasK, TriangleK } kind = SphereK;
+    Point3 center;                 // sphere / disk centre, quad origin, cuboid corner 0, triangle p0
     float radius = 1.0f;
-    Vec3 a{}, b{};                 // quad: side_u, side_v; cuboid: a = corner 1; disk: normal, radial
+    Vec3 a{}, b{};                 // quad: side_u, side_v; cuboid: a = corner 1; disk: normal, radial; triangle: p1, p2
     std::vector<float> P, N, UV;   // mesh; sphere BLAS: P holds (cx, cy, cz, r) per sphere
     std::vector<uint32_t> idx;
 };
@@ -324,6 +324,10 @@ struct Disk {
     Vec3 normal, radial;
     static Disk create(Point3 center, Vec3 normal, Vec3 radial) { return {center, normal, radial}; }
     operator ShapeRef() const { auto s = std::make_shared<Shape>(); s->kind = Shape::DiskK; s->center = center; s->a = normal; s->b = radial; return s; }
+};
+// shape/src/simple.rs:184-195
+struct IsolatedTriangle {
+    static ShapeRef create(Point3 p0, Point3 p1, Point3 p2) { auto s = std::make_shared<Shape>(); s->kind = Shape::TriangleK; s->center = p0; s->a = p1; s->b = p2; return s; }
 };
 // IsoBlas::<Sphere>::build, shape/src/blas.rs:60-69
 struct IsoBlas {
@@ -439,6 +443,7 @@ public:
                     case Shape::QuadK: id = check(pbrs_scene_add_quad(s, sh.center.data(), sh.a.data(), sh.b.data()), "add_quad"); break;
                     case Shape::CuboidK: id = check(pbrs_scene_add_cuboid(s, sh.center.data(), sh.a.data()), "add_cuboid"); break;
                     case Shape::DiskK: id = check(pbrs_scene_add_disk(s, sh.center.data(), sh.a.data(), sh.b.data()), "add_disk"); break;
+                    case Shape::TriangleK: id = check(pbrs_scene_add_triangle(s, sh.center.data(), sh.a.data(), sh.b.data()), "add_triangle"); break;
                     case Shape::SphereBlasK: id = check(pbrs_scene_add_sphere_blas(s, sh.P.data(), uint32_t(sh.P.size() / 4)), "add_sphere_blas"); break;
                     }
                     si = shape_ids.emplace(in.shape.get(), id).first;

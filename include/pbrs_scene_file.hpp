@@ -434,23 +434,21 @@ struct Loader {
             const InstanceTransform &c = ctm.back();
             if (has_area_l && impl == "plymesh") {
                 // parse_samplable_shape, :408-433: one IsolatedTriangle instance and one triangle light
-                // (world-space vertices) per face.  The instance is a one-triangle mesh with the index
-                // triple (0, 2, 1), which undoes TriangleMesh's (i, k, j) swap: same t, same position.
+                // (world-space vertices) per face
                 PlyMesh m = ply(ps);
                 MaterialRef light_mtl = mtl::DiffuseLight::create(area_l);
                 for (size_t f = 0; f + 2 < m.idx.size(); f += 3) {
-                    std::vector<float> tri;
-                    Point3 w[3];
+                    Point3 w[3], o3[3];
                     for (int v = 0; v < 3; ++v) {
                         const float *pv = &m.P[3 * m.idx[f + v]];
-                        tri.insert(tri.end(), {pv[0], pv[1], pv[2]});
+                        o3[v] = {pv[0], pv[1], pv[2]};
                         const float hv[4] = {pv[0], pv[1], pv[2], 1.0f};
                         float o[3];
                         apply(c.fwd, hv, o);  // SamplableShape::transformed_by, light/src/sample_shape.rs:63-68
                         w[v] = {o[0], o[1], o[2]};
                     }
                     area.emplace_back(area_l, light::SamplableShape::Triangle(w[0], w[1], w[2]));
-                    instances.push_back(Instance(shape::TriangleMesh::from_soa(tri, {}, {}, {0, 2, 1}), light_mtl).with_transform(c));
+                    instances.push_back(Instance(shape::IsolatedTriangle::create(o3[0], o3[1], o3[2]), light_mtl).with_transform(c));
                 }
             } else if (has_area_l) {
                 if (impl != "sphere") throw unsupported("samplable shape: " + impl);

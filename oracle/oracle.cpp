@@ -29,6 +29,7 @@ static BBox shape_bbox(const Scene &sc, int shape_id) {
     case SHAPE_QUAD: return quad_bbox(sc.quads[s.index]);
     case SHAPE_CUBOID: return cuboid_bbox(sc.cuboids[s.index]);
     case SHAPE_DISK: return disk_bbox(sc.disks[s.index]);
+    case SHAPE_TRIANGLE: return isotri_bbox(sc.triangles[s.index]);
     default: return mesh_bbox(*sc.meshes[s.index]);
     }
 }
@@ -51,6 +52,9 @@ static bool instance_intersect(const Scene &sc, const Instance &in, const Ray &r
         if (!cuboid_intersect(sc.cuboids[s.index], inv_ray, &hit)) return false;
     } else if (s.kind == SHAPE_DISK) {
         if (!disk_intersect(sc.disks[s.index], inv_ray, &hit)) return false;
+    } else if (s.kind == SHAPE_TRIANGLE) {
+        if (g_diag) g_diag->n_tris++;
+        if (!isotri_intersect(sc.triangles[s.index], inv_ray, &hit)) return false;
     } else {
         if (!mesh_intersect(*sc.meshes[s.index], inv_ray, &hit, &prim)) return false;
     }
@@ -71,6 +75,10 @@ static bool instance_occludes(const Scene &sc, const Instance &in, const Ray &ra
     if (s.kind == SHAPE_QUAD) return quad_occludes(sc.quads[s.index], inv_ray);
     if (s.kind == SHAPE_CUBOID) return cuboid_occludes(sc.cuboids[s.index], inv_ray);
     if (s.kind == SHAPE_DISK) return disk_occludes(sc.disks[s.index], inv_ray);
+    if (s.kind == SHAPE_TRIANGLE) {
+        if (g_diag) g_diag->n_tris++;
+        return isotri_occludes(sc.triangles[s.index], inv_ray);
+    }
     return mesh_occludes(*sc.meshes[s.index], inv_ray);
 }
 
@@ -666,6 +674,11 @@ int oracle_scene_add_disk(oracle_scene *s, const float c[3], const float n[3], c
     if (int rc = make_disk(c, n, rad, &d)) return rc;
     s->sc.disks.push_back(d);
     s->sc.shapes.push_back(ShapeRef{SHAPE_DISK, (int)s->sc.disks.size() - 1});
+    return (int)s->sc.shapes.size() - 1;
+}
+int oracle_scene_add_triangle(oracle_scene *s, const float p0[3], const float p1[3], const float p2[3]) {
+    s->sc.triangles.push_back(IsoTriangle{V3{p0[0], p0[1], p0[2]}, V3{p1[0], p1[1], p1[2]}, V3{p2[0], p2[1], p2[2]}});
+    s->sc.shapes.push_back(ShapeRef{SHAPE_TRIANGLE, (int)s->sc.triangles.size() - 1});
     return (int)s->sc.shapes.size() - 1;
 }
 int oracle_scene_add_sphere_blas(oracle_scene *s, const float *centers_radii, uint32_t n) {

@@ -107,6 +107,8 @@ inline bool intersect_triangle_pred(V3 p0, V3 p1, V3 p2, const Ray &r) {
 struct IsoTriangle {
     V3 p0, p1, p2;
 };
+inline BBox isotri_bbox(const IsoTriangle &t) { return bbox_union_pt(bbox_new(t.p0, t.p1), t.p2); }  // simple.rs:422-424
+inline bool isotri_occludes(const IsoTriangle &t, const Ray &r) { return intersect_triangle_pred(t.p0, t.p1, t.p2, r); }  // :428-430
 inline bool isotri_intersect(const IsoTriangle &t, const Ray &r, Interaction *out) {
     Interaction i;
     if (!intersect_triangle(t.p0, t.p1, t.p2, r, &i)) return false;
@@ -647,7 +649,7 @@ inline Interaction area_shape_sample_towards(const AreaLight &l, const Interacti
 }
 
 // ---------------- instances + TLAS: tlas/src/instance.rs, tlas/src/bvh.rs ----------------
-enum ShapeKind { SHAPE_SPHERE = 0, SHAPE_MESH = 1, SHAPE_QUAD = 2, SHAPE_CUBOID = 3, SHAPE_DISK = 4 };  // a sphere BLAS is a SHAPE_MESH
+enum ShapeKind { SHAPE_SPHERE = 0, SHAPE_MESH = 1, SHAPE_QUAD = 2, SHAPE_CUBOID = 3, SHAPE_DISK = 4, SHAPE_TRIANGLE = 5 };  // a sphere BLAS is a SHAPE_MESH
 struct ShapeRef {
     int kind;
     int index;  // into spheres / meshes
@@ -676,6 +678,7 @@ struct Scene {
     std::vector<Quad> quads;
     std::vector<Cuboid> cuboids;
     std::vector<Disk> disks;
+    std::vector<IsoTriangle> triangles;  // IsolatedTriangle as a Shape (the loader's PLY area lights, loader.rs:408-433)
     std::vector<std::unique_ptr<Mesh>> meshes;
     std::vector<Instance> instances;
     std::vector<DeltaLight> delta_lights;

@@ -113,6 +113,7 @@ SCENE_API = {
     "scene_add_quad": (C.c_int, [P, f3, f3, f3]),
     "scene_add_cuboid": (C.c_int, [P, f3, f3]),
     "scene_add_disk": (C.c_int, [P, f3, f3, f3]),
+    "scene_add_triangle": (C.c_int, [P, f3, f3, f3]),
     "scene_add_sphere_blas": (C.c_int, [P, f3, C.c_uint32]),
     "scene_add_instance": (C.c_int, [P, C.c_int, C.c_int, f3, f3]),
     "scene_add_point_light": (C.c_int, [P, f3, f3]),

@@ -168,6 +168,12 @@ int pbrs_scene_add_disk(pbrs_scene *s, const float center[3], const float normal
     if (int rc = host_make_disk(center, normal, radial, n)) return rc;
     return host_add_simple(s->impl, PBRS_SHAPE_DISK, center, n, radial);
 }
+int pbrs_scene_add_triangle(pbrs_scene *s, const float p0[3], const float p1[3], const float p2[3]) {
+    NEED(s && p0 && p1 && p2, "add_triangle: null argument");
+    NOT_COMMITTED(s);
+    NEED(finite3(p0) && finite3(p1) && finite3(p2), "add_triangle: non-finite argument");
+    return host_add_simple(s->impl, PBRS_SHAPE_TRIANGLE, p0, p1, p2);
+}
 int pbrs_scene_add_sphere_blas(pbrs_scene *s, const float *centers_radii, uint32_t n) {
     NEED(s && centers_radii, "add_sphere_blas: null argument");
     NOT_COMMITTED(s);

@@ -1,4 +1,4 @@
-// ParallelQuad, Cuboid and Disk (shape/src/simple.rs:33-182,291-416) over SimpleRec.
+// ParallelQuad, Cuboid, Disk and IsolatedTriangle (shape/src/simple.rs:33-195,291-431) over SimpleRec.
 //
 // These shapes sit directly under an instance (one per TLAS leaf), so they are met once per walk at
 // most a few times; the three dispatchers at the bottom are deliberately out of line (PB_CALL) so
@@ -140,6 +140,17 @@ PB_DEV bool disk_occludes(vec3 center, vec3 normal, vec3 radial, const Ray &r) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// IsolatedTriangle, simple.rs:418-431: intersect_triangle with (u, v) = (b1, b2) and dpdu = p1 - p0.
+// ---------------------------------------------------------------------------------------------
+PB_DEV bool isotri_shape_intersect(vec3 p0, vec3 p1, vec3 p2, const Ray &r, Isect &out, Diag &dg) {
+    TriHit h;
+    if (!tri_intersect(p0, p1, p2, r, h, dg)) return false;
+    out = isect_new(h.pos, h.t, h.b1, h.b2, h.normal, -r.d, dg);
+    with_dpdu(out, p1 - p0, dg);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dispatch by PBRS_SHAPE_* (out of line on purpose, see the header comment).
 // ---------------------------------------------------------------------------------------------
 PB_CALL bool simple_hit_t(const SimpleRec *rec, uint32_t kind, const Ray &r, float &t, Diag &dg) {
@@ -156,11 +167,18 @@ PB_CALL bool simple_hit_t(const SimpleRec *rec, uint32_t kind, const Ray &r, flo
         t = h.t;
         return true;
     }
+    if (kind == PBRS_SHAPE_TRIANGLE) {
+        TriHit h;
+        if (!tri_intersect(s.a, s.b, s.c, r, h, dg)) return false;
+        t = h.t;
+        return true;
+    }
     vec3 p;
     return disk_hit(s.a, s.b, s.c, r, t, p);
 }
-PB_CALL bool simple_occludes(const SimpleRec *rec, uint32_t kind, const Ray &r) {
+PB_CALL bool simple_occludes(const SimpleRec *rec, uint32_t kind, const Ray &r, Diag &dg) {
     const Simple s = load_simple(rec);
+    if (kind == PBRS_SHAPE_TRIANGLE) return tri_occludes(s.a, s.b, s.c, r, dg);
     if (kind == PBRS_SHAPE_QUAD) return quad_occludes(s.a, s.b, s.c, r);
     if (kind == PBRS_SHAPE_CUBOID) return cuboid_occludes(s.a, s.b, r);
     return disk_occludes(s.a, s.b, s.c, r);
@@ -169,6 +187,7 @@ PB_CALL bool simple_intersect(const SimpleRec *rec, uint32_t kind, const Ray &r,
     const Simple s = load_simple(rec);
     if (kind == PBRS_SHAPE_QUAD) return quad_intersect(s.a, s.b, s.c, r, out, dg);
     if (kind == PBRS_SHAPE_CUBOID) return cuboid_intersect(s.a, s.b, r, out, dg);
+    if (kind == PBRS_SHAPE_TRIANGLE) return isotri_shape_intersect(s.a, s.b, s.c, r, out, dg);
     return disk_intersect(s.a, s.b, s.c, r, out, dg);
 }
 

@@ -308,7 +308,8 @@ struct Walk {
             } else if (!EXT) {
                 hit = false;  // unreachable: has_ext selects the EXT kernels
             } else {  // quad, cuboid, disk: shape/src/simple.rs
-                hit = ANY ? simple_occludes(sc.simples + index, kind, obj) : simple_hit_t(sc.simples + index, kind, obj, t, dg);
+                if (COUNT && kind == PBRS_SHAPE_TRIANGLE) tc.tris++;
+                hit = ANY ? simple_occludes(sc.simples + index, kind, obj, dg) : simple_hit_t(sc.simples + index, kind, obj, t, dg);
             }
             if (ANY) {
                 if (hit) { occluded = true; done = true; }

@@ -77,6 +77,7 @@ static_assert(sizeof(SphereRec) == 16, "SphereRec must be 16 bytes");
 //   quad:   a = origin, b = side_u, c = side_v
 //   cuboid: a = min,    b = max
 //   disk:   a = centre, b = normal (unit), c = radial
+//   isolated triangle: a = p0, b = p1, c = p2
 struct SimpleRec {
     float a[3]; uint32_t pad0;
     float b[3]; uint32_t pad1;
@@ -89,6 +90,7 @@ static_assert(sizeof(SimpleRec) == 48, "SimpleRec must be 48 bytes");
 #define PBRS_SHAPE_QUAD 2u
 #define PBRS_SHAPE_CUBOID 3u
 #define PBRS_SHAPE_DISK 4u
+#define PBRS_SHAPE_TRIANGLE 5u  // IsolatedTriangle: a = p0, b = p1, c = p2
 
 // Row r of a 3x4 matrix = (c0[r], c1[r], c2[r], c3[r]) of the reference's column Mat4.
 struct InstTravRec {

@@ -422,6 +422,11 @@ static HostBox simple_box(uint32_t kind, const SimpleRec &r) {
         return box_merge(box_of_points(r.a, ou), box_of_points(ov, ouv));
     }
     if (kind == PBRS_SHAPE_CUBOID) return box_of_points(r.a, r.b);  // :339-341
+    if (kind == PBRS_SHAPE_TRIANGLE) {  // :422-424: BBox::new(p0, p1).union(p2)
+        HostBox b = box_of_points(r.a, r.b);
+        box_grow_point(b, r.c);
+        return b;
+    }
     // Disk, :298-305: make_coord_system(normal) scaled by |radial|
     float v1[3], v2[3];
     host_make_coord_system(r.b, v1, v2);

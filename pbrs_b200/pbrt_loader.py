@@ -640,16 +640,14 @@ class Loader:
             ctm = self.ctm[-1]
             if self.area_l is not None and impl == "plymesh":
                 # parse_samplable_shape, :408-433: one IsolatedTriangle instance + one triangle area
-                # light (world-space vertices) per face.  The instance is a one-triangle mesh whose
-                # index triple (0, 2, 1) undoes TriangleMesh's (i, k, j) swap, so t and the hit
-                # position are the IsolatedTriangle's bit for bit.
+                # light (world-space vertices) per face
                 P, _, _, idx = self.ply(ps)
                 light_mtl = self.sd.diffuse_light(self.area_l)
                 for i, j, k in idx:
                     tri = P[[i, j, k]]
                     w = [tuple(float(c) for c in ctm.apply_point(v)) for v in tri]  # transformed_by, sample_shape.rs:63-68
                     self.sd.add_area_light_triangle(w[0], w[1], w[2], self.area_l)
-                    self.instances.append((self.sd.add_mesh(tri, np.array([[0, 2, 1]], np.uint32)), light_mtl, ctm))
+                    self.instances.append((self.sd.add_triangle(*(tuple(float(c) for c in v) for v in tri)), light_mtl, ctm))
             elif self.area_l is not None:
                 if impl != "sphere":
                     raise PbrtError(f"samplable shape: {impl} is unimplemented!() upstream (only sphere / plymesh)")

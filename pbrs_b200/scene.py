@@ -146,6 +146,12 @@ class SceneDesc:
         self.n_shape += 1
         return self.n_shape - 1
 
+    def add_triangle(self, p0, p1, p2):
+        """IsolatedTriangle::new (shape/src/simple.rs:184-195)."""
+        self.ops.append(("scene_add_triangle", (p0, p1, p2)))
+        self.n_shape += 1
+        return self.n_shape - 1
+
     def add_sphere_blas(self, centers_radii):
         """IsoBlas::<Sphere>::build: an (n, 4) array of (cx, cy, cz, radius)."""
         cr = np.ascontiguousarray(centers_radii, dtype=np.float32).reshape(-1, 4)

@@ -29,6 +29,7 @@ def _add_simple_shapes(sd, mats, seed):
         r32 = r.astype(np.float32)
         if abs(float(np.dot(r32, n32 / np.linalg.norm(n32)))) < 5e-7:   # Disk::new asserts |radial . n| < 1e-6
             shapes.append(sd.add_disk(tuple(rng.uniform(-1.5, 1.5, 3)), tuple(n32), tuple(r32)))
+    shapes.append(sd.add_triangle(*(tuple(v) for v in rng.uniform(-1.5, 1.5, (3, 3)))))
     nb = int(rng.choice([1, 3, 4, 5, 17, 60]))
     shapes.append(sd.add_sphere_blas(np.concatenate([rng.uniform(-1.2, 1.2, (nb, 3)), rng.uniform(0.05, 0.5, (nb, 1))], axis=1)))
     for sh in shapes:

@@ -177,7 +177,7 @@ def test_plymesh_scene_equals_constructor_scene(tmp_path, oracle_api, hostsim_ap
     sd = load_pbrt(path)
     h = sd.realize(hostsim_api)
     info = h.info()
-    assert (info.n_instances, info.n_meshes, info.n_triangles, info.n_lights) == (4, 4, 3 + 80 + 2, 3)
+    assert (info.n_instances, info.n_meshes, info.n_triangles, info.n_lights) == (4, 2, 3 + 80, 3)
     # the same scene through the constructors
     from pbrs_b200.scene import SceneDesc
     ref = SceneDesc()
@@ -195,7 +195,7 @@ def test_plymesh_scene_equals_constructor_scene(tmp_path, oracle_api, hostsim_ap
     for tri in idx:
         w = [tuple(float(c) for c in t.apply_point(P[v])) for v in tri]
         ref.add_area_light_triangle(w[0], w[1], w[2], L)
-        ref.add_instance(ref.add_mesh(P[tri], np.array([[0, 2, 1]], np.uint32)), lm, fwd=t.fwd, inv=t.inv)
+        ref.add_instance(ref.add_triangle(*(tuple(float(c) for c in P[v]) for v in tri)), lm, fwd=t.fwd, inv=t.inv)
     a, b = h.render_ids(0, msaa=1), ref.realize(hostsim_api).render_ids(0, msaa=1)
     assert (a[0] != 0xFFFFFFFF).mean() > 0.4
     # instance numbering differs (the loader appends lights in file order too, so it does not), ids equal

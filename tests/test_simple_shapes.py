@@ -144,6 +144,29 @@ def test_disk_rejects_what_the_reference_asserts(oracle_api, hostsim_api):
             sd.realize(api)
 
 
+def test_isolated_triangle_known_answers(oracle_api):
+    # IsolatedTriangle::intersect = intersect_triangle + with_dpdu(p1 - p0) (simple.rs:425-427):
+    # (u, v) are the barycentrics of p1 and p2, the normal faces the ray
+    from oracle import oracle_ffi as O
+    h = _single(lambda sd: sd.add_triangle((0.0, 0.0, 0.0), (2.0, 0.0, 0.0), (0.0, 2.0, 0.0))).realize(oracle_api)
+    out = O.trace_ray(h, (0.5, 1.0, -3.0), (0.0, 0.0, 1.0))
+    assert out[0] == 1.0 and out[15] == 0.0
+    np.testing.assert_allclose(out[1], 3.0)
+    np.testing.assert_allclose(out[2:5], (0.5, 1.0, 0.0), atol=1e-6)
+    np.testing.assert_allclose(out[5:8], (0.0, 0.0, -1.0), atol=1e-7)
+    np.testing.assert_allclose(out[8:10], (0.25, 0.5), atol=1e-6)
+    np.testing.assert_allclose(out[12:15], (1.0, 0.0, 0.0), atol=1e-6)
+    assert O.trace_ray(h, (1.5, 1.5, -3.0), (0.0, 0.0, 1.0))[0] == 0.0            # outside the hypotenuse
+    assert O.occludes_ray(h, (0.5, 1.0, -3.0), (0.0, 0.0, 1.0)) == 1
+    assert O.occludes_ray(h, (0.5, 1.0, -3.0), (0.0, 0.0, 1.0), t_max=2.0) == 0
+    # the same triangle as a one-triangle TriangleMesh listed (0, 2, 1): the mesh swaps (i, k, j) back,
+    # so t and the position are bit-identical (the mesh's uv / tangent are its own)
+    m = _single(lambda sd: sd.add_mesh(np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0]], np.float32), np.array([[0, 2, 1]], np.uint32))).realize(oracle_api)
+    for o, d in [((0.5, 1.0, -3.0), (0.1, -0.05, 1.0)), ((0.3, 0.2, 4.0), (0.02, 0.1, -1.0))]:
+        a, b = O.trace_ray(h, o, d), O.trace_ray(m, o, d)
+        assert a[0] == b[0] == 1.0 and bits_equal(a[1:8], b[1:8]).all()
+
+
 def test_sphere_blas_equals_individual_spheres_where_unambiguous(oracle_api):
     # The same spheres as one IsoBlas instance and as separate instances: primary hits agree on t
     # and, through prim / instance id, on the sphere -- except where two spheres overlap along
@@ -182,6 +205,8 @@ def _cases():
         "cuboid_shear": (lambda sd: sd.add_cuboid((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)), shear, (0.5, 0.5, -5.0)),
         "disk": (lambda sd: sd.add_disk((0.0, 0.0, 0.0), (0.2, 0.3, -1.0), (1.5, 0.0, 0.3)), None, (0.0, 0.0, -5.0)),
         "disk_rot": (lambda sd: sd.add_disk((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), (1.0, 1.0, 0.0)), rot, (0.0, 0.0, -5.0)),
+        "triangle": (lambda sd: sd.add_triangle((-1.5, -1.0, 0.2), (1.6, -0.8, -0.3), (0.1, 1.7, 0.4)), None, (0.0, 0.0, -5.0)),
+        "triangle_shear": (lambda sd: sd.add_triangle((-1.5, -1.0, 0.0), (1.5, -1.0, 0.0), (0.0, 1.5, 0.0)), shear, (0.3, 0.2, -5.0)),
         "balls": (lambda sd: sd.add_sphere_blas(balls), rot, (0.0, 0.0, -6.0)),
         "four_balls": (lambda sd: sd.add_sphere_blas(balls[:4]), None, (0.0, 0.0, -6.0)),   # the root is a leaf
     }

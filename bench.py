@@ -281,9 +281,12 @@ def main():
         api["render"](h.ptr, C.byref(o), hp, None)
     barrier()
     t0 = time.perf_counter()
+    step_times = []
     for _ in range(args.steps):
+        t_step = time.perf_counter()
         rc = api["render"](h.ptr, C.byref(o), hp, None)
         assert rc == 0, h.last_error()
+        step_times.append((time.perf_counter() - t_step) * 1e3)
         if world > 1:
             # host-side combine of the ranks' films: stage through the device film and NCCL
             film.copy_(torch.from_numpy(host), non_blocking=False)
@@ -292,6 +295,8 @@ def main():
                 host[...] = film.cpu().numpy()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("PBRS_BENCH_DEBUG"):
+        print("e2e per-step ms:", " ".join(f"{t:.2f}" for t in step_times), file=sys.stderr)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

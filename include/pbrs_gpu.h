@@ -183,6 +183,7 @@ typedef enum pbrs_split {
 #define PBRS_FLAG_TIME_STAGES 2u     /* fill ms_* with CUDA-event timings per stage */
 #define PBRS_FLAG_NO_JITTER 4u       /* jitter (0,0) as the visualizers do, src/main.rs:170 */
 #define PBRS_FLAG_RAW_SUM 8u         /* leave the film as the un-normalised sample sum */
+#define PBRS_FLAG_NO_GRAPH 16u       /* enqueue a small frame kernel by kernel instead of replaying its CUDA graph */
 
 typedef struct pbrs_render_opts {
     int32_t integrator;  /* pbrs_integrator */

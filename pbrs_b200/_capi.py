@@ -18,7 +18,7 @@ MTL_DIFFUSE_LIGHT, MTL_PLASTIC, MTL_UBER, MTL_SUBSTRATE = 5, 6, 7, 8
 ENV_BLUE_SKY, ENV_DARK_ROOM, ENV_DUSK = 0, 1, 2
 INTEGRATOR_DIRECT, INTEGRATOR_PATH = 0, 1
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
-FLAG_COUNT_TRAVERSAL, FLAG_TIME_STAGES, FLAG_NO_JITTER, FLAG_RAW_SUM = 1, 2, 4, 8
+FLAG_COUNT_TRAVERSAL, FLAG_TIME_STAGES, FLAG_NO_JITTER, FLAG_RAW_SUM, FLAG_NO_GRAPH = 1, 2, 4, 8, 16
 
 ERR_INVALID_ARG, ERR_STATE, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_OOM = -1, -2, -3, -4, -5, -6
 

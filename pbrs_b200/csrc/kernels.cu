@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -396,6 +397,12 @@ struct Workspace {
     int sms = 0;
     Grid grid{};
     bool grid_ready = false;
+    // Small frames are launch-bound (C2: ~20 dependent launches against 0.8 ms of work), so their
+    // whole enqueue sequence -- memsets, the fork onto the lanes, every kernel, the join -- is
+    // captured once per distinct parameter set and replayed as one CUDA graph.
+    cudaStream_t graph_stream = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_key;
 };
 
 void workspace_free(Workspace *w) {
@@ -409,6 +416,8 @@ void workspace_free(Workspace *w) {
     if (w->stats) cudaFree(w->stats);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     for (auto &e : w->stage_ev) cudaEventDestroy(e);
+    if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
+    if (w->graph_stream) cudaStreamDestroy(w->graph_stream);
     delete w;
 }
 
@@ -438,6 +447,7 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
     if (!w.lane_stream[0]) {
         for (int l = 0; l < 2; ++l) { CK(cudaStreamCreateWithFlags(&w.lane_stream[l], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.join_ev[l], cudaEventDisableTiming)); }
         CK(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&w.graph_stream, cudaStreamNonBlocking));
     }
     if (w.capacity < capacity || w.n_lanes < n_lanes) {
         for (auto &p : w.slab) if (p) { cudaFree(p); p = nullptr; }
@@ -545,19 +555,25 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
 
     if (fp.n_tiles) CK(cudaMemcpyAsync(w.tiles, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, stream));
     fp.tiles = w.tiles;
-    CK(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * kStatCount, stream));
-    if (n_batches) CK(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * PBRS_COUNTS_PER_BATCH * (size_t)n_batches, stream));
-    if (tg.film) CK(cudaMemsetAsync(tg.film, 0, sizeof(float) * 3 * (size_t)W * H, stream));
     if (want_stats) CK(cudaEventRecord(w.ev[0], stream));
 
     uint64_t launches = 0, launches_extend = 0, launches_shadow = 0;
     const DeviceScene &sc = s.dscene;
+    const bool time_stages = want_stats && (o.flags & PBRS_FLAG_TIME_STAGES) != 0;
+    std::vector<int> ev_kind;
+    enum { T_GEN = 0, T_EXT = 1, T_SHADE = 2, T_SHADOW = 3, T_ACC = 4 };
+    size_t ev_used = 0;
+    // Everything the frame puts on the GPU, on `origin` (and, forked from it, the lane streams).
+    auto enqueue = [&](cudaStream_t origin) -> int {
+    cudaStream_t stream = origin;
+    cudaStream_t const caller_stream = origin;
+    launches = launches_extend = launches_shadow = 0;
+    CK(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * kStatCount, stream));
+    if (n_batches) CK(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * PBRS_COUNTS_PER_BATCH * (size_t)n_batches, stream));
+    if (tg.film) CK(cudaMemsetAsync(tg.film, 0, sizeof(float) * 3 * (size_t)W * H, stream));
     // PBRS_FLAG_TIME_STAGES: one event after every launch; stage time = sum of the gaps that end
     // with a launch of that stage (the stream is in order, so a gap is that kernel's duration).
-    const bool time_stages = want_stats && (o.flags & PBRS_FLAG_TIME_STAGES) != 0;
-    enum { T_GEN = 0, T_EXT = 1, T_SHADE = 2, T_SHADOW = 3, T_ACC = 4 };
-    std::vector<int> ev_kind;
-    size_t ev_used = 0;
+
     auto mark = [&](int kind) -> int {
         if (!time_stages) return 0;
         if (ev_used == w.stage_ev.size()) {
@@ -611,9 +627,65 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
             if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; mark(T_ACC); }
         }
     }
-    stream = caller_stream;
     if (n_lanes > 1)
         for (int l = 0; l < n_lanes; ++l) { CK(cudaEventRecord(w.join_ev[l], w.lane_stream[l])); CK(cudaStreamWaitEvent(caller_stream, w.join_ev[l], 0)); }
+    return 0;
+    };  // enqueue
+
+    // a frame of a few batches is replayed from its graph; large frames (hundreds of batches of
+    // millisecond kernels) gain nothing from it and are enqueued directly
+    static const bool env_no_graph = std::getenv("PBRS_NO_GRAPH") != nullptr;  // development knob for A/B runs
+    const bool use_graph = !time_stages && !env_no_graph && !(o.flags & PBRS_FLAG_NO_GRAPH) && n_batches >= 1 && n_batches <= 8;
+    if (use_graph) {
+        std::vector<unsigned char> key;
+        auto put = [&key](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; key.insert(key.end(), b, b + n); };
+        const uint32_t shape[8] = {n_batches, ppb, capacity, (uint32_t)n_stages, (uint32_t)n_lanes, count_trav ? 1u : 0u, (uint32_t)o.integrator, 0u};
+        FrameParams fpk;
+        std::memset(&fpk, 0, sizeof fpk);  // field by field: padding bytes must not enter the key
+        fpk.seed = fp.seed; fpk.msaa = fp.msaa; fpk.spp = fp.spp; fpk.spp_r = fp.spp_r; fpk.rank = fp.rank; fpk.world = fp.world;
+        fpk.split_samples = fp.split_samples; fpk.only_sample = fp.only_sample; fpk.integrator = fp.integrator; fpk.max_depth = fp.max_depth;
+        fpk.flags = fp.flags; fpk.x0 = fp.x0; fpk.y0 = fp.y0; fpk.x1 = fp.x1; fpk.y1 = fp.y1; fpk.width = fp.width; fpk.height = fp.height;
+        fpk.tiles = fp.tiles; fpk.n_tiles = fp.n_tiles;
+        put(shape, sizeof shape); put(&fpk, sizeof fpk); put(&total_pixels, sizeof total_pixels);
+        const void *ptrs[12] = {tg.film, tg.samples, tg.ids_inst, tg.ids_prim, tg.ids_t, w.slab[0], w.slab[1], w.counts, w.stats, w.tiles,
+                                s.dscene.tlas_nodes, s.dscene.inst_trav};
+        put(ptrs, sizeof ptrs);
+        if (!w.graph_exec || key != w.graph_key) {
+            if (w.graph_exec) { cudaGraphExecDestroy(w.graph_exec); w.graph_exec = nullptr; }
+            CK(cudaStreamBeginCapture(w.graph_stream, cudaStreamCaptureModeThreadLocal));
+            const int erc = enqueue(w.graph_stream);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ee = cudaStreamEndCapture(w.graph_stream, &g);
+            if (erc < 0 || ee != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                if (erc < 0) return erc;
+                set_error(std::string("graph capture: ") + cudaGetErrorString(ee));
+                return PBRS_ERR_CUDA;
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&w.graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { w.graph_exec = nullptr; set_error(std::string("graph instantiate: ") + cudaGetErrorString(ie)); return PBRS_ERR_CUDA; }
+            w.graph_key = key;
+        } else {
+            // the counters the capture pass would have produced
+            for (uint32_t b = 0; b < n_batches; ++b) {
+                ++launches;
+                for (int stage = 0; stage < n_stages; ++stage) {
+                    ++launches; ++launches_extend;
+                    if (tg.only_sample >= 0) break;
+                    launches += PBRS_NUM_CLS + 1; ++launches_shadow;
+                }
+                if (tg.only_sample >= 0) ++launches;
+                else launches += (tg.film ? 1 : 0) + (tg.samples ? 1 : 0);
+            }
+        }
+        CK(cudaGraphLaunch(w.graph_exec, caller_stream));
+    } else {
+        const int erc = enqueue(caller_stream);
+        if (erc < 0) return erc;
+    }
+    stream = caller_stream;
     CK(cudaGetLastError());
     if (want_stats) {
         CK(cudaEventRecord(w.ev[1], stream));

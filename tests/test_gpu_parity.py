@@ -139,6 +139,31 @@ def test_properties_at_full_c1_size(gpu_api):
     assert (crop[:200] == 0).all()
 
 
+def test_graph_replay_equals_direct_enqueue(gpu_api):
+    """Frames of a few batches are captured once and replayed as a CUDA graph (kernels.cu): same
+    film as enqueuing kernel by kernel (PBRS_FLAG_NO_GRAPH), replay after replay, and a changed
+    option set is a new capture, not a stale replay."""
+    import torch
+    from pbrs_b200 import _capi as K
+    h = scenes.cornell_box(256, 192).realize(gpu_api)
+    for kw in (dict(integrator="path", msaa=2), dict(integrator="direct", msaa=1), dict(integrator="path", msaa=3, paths_in_flight=200_000)):
+        direct, sd = h.render(flags=K.FLAG_NO_GRAPH, **kw)
+        for _ in range(3):
+            g, sg = h.render(**kw)
+            assert bits_equal(g, direct).all(), kw
+            assert (sg["n_samples"], sg["n_rays_extend"], sg["n_rays_shadow"], sg["launches"]) == \
+                   (sd["n_samples"], sd["n_rays_extend"], sd["n_rays_shadow"], sd["launches"])
+    # the same graph on a caller's stream and film
+    film = torch.empty((192, 256, 3), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    want, _ = h.render(integrator="path", msaa=2, flags=K.FLAG_NO_GRAPH)
+    for _ in range(2):
+        film.zero_()
+        h.render_device(film.data_ptr(), stream=s.cuda_stream, integrator="path", msaa=2)
+        s.synchronize()
+        assert bits_equal(film.cpu().numpy(), want).all()
+
+
 def test_render_device_keeps_the_film_on_the_gpu(gpu_api):
     import torch
     h = scenes.cornell_box(128, 128).realize(gpu_api)

@@ -189,6 +189,36 @@ def test_mesh_scale_walk_matches_oracle(oracle_api, gpu_api):
     assert_stats_close(sb, sa, "terrain film", rel=1e-3)
 
 
+def test_full_size_c4_scene_properties_and_oracle_crop(oracle_api, gpu_api):
+    """The headline workload's own scene (1,002,528-triangle terrain, 3840x2160) at 1 spp: the
+    oracle agrees on a crop (ids bit-exact, per-sample radiance, counters), and the full frame has
+    the size-independent properties: deterministic, independent of the batch size, a 2-rank tile
+    split sums to it bit-exactly, a crop is its sub-rectangle."""
+    sd = scenes.mesh_terrain()
+    hg, ho = sd.realize(gpu_api), sd.realize(oracle_api)
+    assert hg.info().n_triangles > 1_000_000
+    crop = (1700, 1200, 96, 64)
+    a, b = ho.render_ids(0, msaa=1, crop=crop), hg.render_ids(0, msaa=1, crop=crop)
+    assert (a[0] != 0xFFFFFFFF).mean() > 0.9
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and bits_equal(a[2], b[2]).all()
+    fa, sa = ho.render_samples(integrator="path", msaa=1, max_depth=5, flags=1, crop=crop)
+    fb, sb = hg.render_samples(integrator="path", msaa=1, max_depth=5, flags=1, crop=crop)
+    assert_radiance_close(fb, fa, "C4 crop", outliers=1e-3)
+    assert_stats_close(sb, sa, "C4 crop", rel=1e-3)
+    full, st = hg.render(integrator="path", msaa=1)
+    assert st["n_samples"] == 3840 * 2160
+    again, _ = hg.render(integrator="path", msaa=1, paths_in_flight=1_500_000)
+    assert bits_equal(full, again).all()
+    t0, _ = hg.render(integrator="path", msaa=1, rank=0, world_size=2, split="tiles")
+    t1, _ = hg.render(integrator="path", msaa=1, rank=1, world_size=2, split="tiles")
+    assert bits_equal(t0 + t1, full).all() and ((t0 == 0) | (t1 == 0)).all()
+    sub, _ = hg.render(integrator="path", msaa=1, crop=crop)
+    x, y, w, h = crop
+    assert bits_equal(sub[y:y + h, x:x + w], full[y:y + h, x:x + w]).all()
+    # the film of the crop equals the mean of the oracle's samples there (1 spp: the sample itself)
+    assert_radiance_close(full[y:y + h, x:x + w], fa[:, :, 0, :], "C4 film vs oracle samples", outliers=1e-3)
+
+
 def test_instanced_walk_matches_oracle(oracle_api, gpu_api):
     """TLAS of 1600 transformed instances: the recursive closest-hit emulation incl. extent quirks."""
     sd = scenes.instanced_field(480, 270, n_side=40, n_meshes=5, ico_subdiv=2, n_lights=8)

@@ -124,7 +124,7 @@ class ClockSampler:
         return out
 
 
-def cpu_sample(handle, integrator, msaa, target_s=12.0):
+def cpu_sample(handle, integrator, msaa, target_s=24.0):
     """Times the oracle on rows y0, y0+step, ... of the frame, step chosen for ~target_s of CPU work."""
     from oracle import oracle_ffi
     H, W = handle.height, handle.width

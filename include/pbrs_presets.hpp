@@ -111,6 +111,44 @@ inline Scene plates() {
     return Scene(std::move(inst), camera).with_lights({}, std::move(area));
 }
 
+// preset::everything, scene/src/preset.rs:360-442: a floor of 400 random-height Cuboids, a quad
+// light, glass / metal / textured spheres and a rotated IsoBlas of 1000 small spheres.  Seeded
+// draws in place of rand_f32(); a generated checker stands in for assets/earthmap.png.
+inline Scene everything() {
+    uint64_t state = 0x5EEDull;
+    auto rnd = [&]() { state = state * 6364136223846793005ull + 1442695040888963407ull; return float((state >> 40) & 0xFFFFFF) / 16777216.0f; };
+    MaterialRef ground = mtl::Lambertian::solid({0.48f, 0.83f, 0.53f});
+    std::vector<Instance> inst;
+    for (int i = 0; i < 20; ++i)
+        for (int j = 0; j < 20; ++j) {
+            const float x0 = -1000.0f + float(i) * 100.0f, z0 = -1000.0f + float(j) * 100.0f, y1 = rnd() * 100.0f + 1.0f;
+            inst.emplace_back(shape::Cuboid::from_points(point3(x0, 0.0f, z0), point3(x0 + 100.0f, y1, z0 + 100.0f)), ground);
+        }
+    const Color L = Color::gray(7.0f);
+    const shape::ParallelQuad light_quad = shape::ParallelQuad::new_xz({123, 423}, 554, {147, 412});
+    inst.emplace_back(light_quad, mtl::DiffuseLight::create(L));
+    inst.emplace_back(shape::Sphere::from_raw(260, 150, 45, 50), mtl::Dielectric::create(1.5f));
+    const Color silver_r{0.155184f, 0.116681f, 0.138360f}, silver_i{4.828131f, 3.122411f, 2.147082f};  // preset.rs:467-472
+    inst.emplace_back(shape::Sphere::from_raw(0, 150, 145, 50), mtl::Metal::from_ior(silver_r, silver_i, 1.0f));
+    inst.emplace_back(shape::Sphere::from_raw(360, 150, 145, 70), mtl::Dielectric::create(1.5f));
+    std::vector<uint8_t> img(256 * 256 * 3);
+    for (int y = 0; y < 256; ++y)
+        for (int x = 0; x < 256; ++x) {
+            const bool c = ((x / 16) + (y / 16)) % 2 != 0;
+            uint8_t *p = &img[3 * (y * 256 + x)];
+            p[0] = c ? 190 : 70; p[1] = c ? 160 : 115; p[2] = c ? 95 : 55;
+        }
+    inst.emplace_back(shape::Sphere::from_raw(400, 200, 400, 100), mtl::Lambertian::textured(tex::Image::from_rgb8(256, 256, img)));
+    inst.emplace_back(shape::Sphere::from_raw(220, 280, 300, 80), mtl::Lambertian::textured(tex::Perlin::with_freq(10.0f)));
+    std::vector<shape::IsoBlas::Ball> balls(1000);
+    for (auto &b : balls) b = {point3(rnd() * 165.0f, rnd() * 165.0f, rnd() * 165.0f), 10.0f};
+    inst.push_back(Instance(shape::IsoBlas::build(balls), mtl::Lambertian::solid(Color::gray(0.73f)))
+                       .with_transform(AffineTransform::translater({-100, 270, 395}) * AffineTransform::rotater(Vec3::Y(), Angle::new_deg(15))));
+    Camera camera({800, 800}, Angle::new_deg(40.0f));
+    camera.look_at(point3(478, 278, -600), point3(278, 278, 0), Vec3::Y());
+    return Scene(std::move(inst), camera).with_fn_env_light(light::EnvFn::DarkRoom).with_lights({}, {light::DiffuseAreaLight(L, light::SamplableShape::Quad(light_quad))});
+}
+
 // The C1 workload of bench.py: the same box with triangle walls and a sphere light (what the
 // loader can express, scene/src/loader.rs:396-434).
 inline Scene cornell_box_mesh() {

@@ -921,9 +921,11 @@ int oracle_scene_get_info(const oracle_scene *s, pbrs_scene_info *info) {
     info->width = sc.camera.width; info->height = sc.camera.height;
     info->n_instances = (uint32_t)sc.instances.size();
     info->n_meshes = (uint32_t)sc.meshes.size();
-    info->n_spheres = (uint32_t)sc.spheres.size();
-    uint32_t nt = 0;
-    for (auto &m : sc.meshes) nt += (uint32_t)m->tris.size();
+    uint32_t nt = 0, nb = 0;
+    for (auto &m : sc.meshes) {
+        if (m->balls.empty()) nt += (uint32_t)m->tris.size(); else nb += (uint32_t)m->balls.size();
+    }
+    info->n_spheres = (uint32_t)sc.spheres.size() + nb;  // incl. the spheres of sphere BLASes
     info->n_triangles = nt;
     info->n_tlas_nodes = sc.n_tlas_inner;
     info->n_lights = (uint32_t)(sc.delta_lights.size() + sc.area_lights.size() + (has_env_light(sc) ? 1 : 0));

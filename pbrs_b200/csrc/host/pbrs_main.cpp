@@ -1,7 +1,7 @@
 // pbrs_main -- the reference's driver (src/main.rs:56-246) with the B200 back end behind it.
 //
 //   pbrs_main --pbrt_file scene.pbrt [--integrator direct|path] [--msaa N]
-//   pbrs_main --scene_name cornell_box|cornell_box_mesh|125_spheres|quad|quad_light|plates|two_perlin_spheres ...
+//   pbrs_main --scene_name cornell_box|cornell_box_mesh|125_spheres|quad|quad_light|plates|two_perlin_spheres|everything ...
 //
 // Same command-line keys as src/cli_options.rs:52-59 (--use_multi_thread / --use_single_thread are
 // accepted and ignored: there is one GPU path; --visualize_* are debug views outside the hot path).
@@ -76,8 +76,9 @@ int main(int argc, char **argv) {
             if (options.scene_name == "quad") return preset::quad_scene();
             if (options.scene_name == "quad_light") return preset::quad_light();
             if (options.scene_name == "plates") return preset::plates();
+            if (options.scene_name == "everything") return preset::everything();
             if (options.scene_name == "two_perlin_spheres") return preset::two_perlin_spheres();
-            std::fprintf(stderr, "No scene file or name specified. Abort.\nAvailable scenes: 125_spheres | cornell_box | cornell_box_mesh | quad | quad_light | plates | two_perlin_spheres\n");
+            std::fprintf(stderr, "No scene file or name specified. Abort.\nAvailable scenes: 125_spheres | cornell_box | cornell_box_mesh | quad | quad_light | plates | two_perlin_spheres | everything\n");
             std::exit(1);
         }();
         auto t0 = std::chrono::steady_clock::now();

@@ -462,7 +462,7 @@ int host_add_instance(SceneImpl &s, int shape, int mtl, const float *fwd, const 
 
 int host_build(SceneImpl &s) {
     // ---- BLAS per mesh ----
-    uint32_t total_nodes = 0, total_tris = 0;
+    uint32_t total_nodes = 0, total_tris = 0, total_balls = 0;
     for (HostMesh &m : s.meshes) {
         const bool is_balls = !m.balls.empty();
         size_t nt = is_balls ? m.balls.size() : m.idx.size() / 3;
@@ -485,7 +485,7 @@ int host_build(SceneImpl &s) {
         m.root_box = root.box;
         m.root_is_leaf = root.leaf;
         total_nodes += (uint32_t)m.nodes.size();
-        total_tris += (uint32_t)nt;
+        if (is_balls) total_balls += (uint32_t)nt; else total_tris += (uint32_t)nt;
     }
     // ---- instance boxes (tlas/src/instance.rs:47-49) ----
     for (HostInstance &in : s.instances) {
@@ -522,7 +522,7 @@ int host_build(SceneImpl &s) {
     s.info.height = s.cam.height;
     s.info.n_instances = (uint32_t)s.instances.size();
     s.info.n_meshes = (uint32_t)s.meshes.size();
-    s.info.n_spheres = (uint32_t)s.spheres.size();
+    s.info.n_spheres = (uint32_t)s.spheres.size() + total_balls;  // incl. the spheres of sphere BLASes
     s.info.n_triangles = total_tris;
     s.info.n_tlas_nodes = (uint32_t)s.tlas_nodes.size();
     s.info.n_blas_nodes = total_nodes;

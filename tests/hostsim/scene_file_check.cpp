@@ -19,6 +19,7 @@ int main(int argc, char **argv) {
                          : what == "preset:quad" ? pbrs::preset::quad_scene()
                          : what == "preset:quad_light" ? pbrs::preset::quad_light()
                          : what == "preset:plates" ? pbrs::preset::plates()
+                         : what == "preset:everything" ? pbrs::preset::everything()
                          : what == "preset:cornell_box_mesh" ? pbrs::preset::cornell_box_mesh()
                                                              : pbrs::scene_file::build_scene(what);
         pbrs_scene *s = sc.commit();

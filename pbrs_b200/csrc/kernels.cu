@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 const bool adv = busy && w.advancing();
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, adv);
                 const unsigned waiting = __ballot_sync(0xFFFFFFFFu, busy && w.at_leaf());
-                if (m == 0u || __popc(waiting) >= kLeafVote<ANY>) break;
+                if (m == 0u || __popc(waiting) >= (ANY ? kLeafVote<true> : (int)sc.leaf_vote)) break;
                 if (adv) w.advance(sc, dg, tc);
             }
         }

@@ -35,6 +35,7 @@ static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
 // number of primitives (1..6; 0 = longer, walk the run by its PBRS_TRI_LAST_IN_LEAF flag), bits
 // 0..27 the first primitive.  The any-hit kernel uses it to spread the triangle tests of all the
 // lanes that stand at a leaf over the whole warp.
+#define PBRS_MANY_INSTANCES 1024u
 #define PBRS_LEAF_FIRST_MASK 0x0FFFFFFFu
 #define PBRS_LEAF_COUNT_SHIFT 28
 #define PBRS_LEAF_COUNT_MAX 6u
@@ -214,6 +215,7 @@ struct DeviceScene {
     float tlas_min[3], tlas_max[3];
     uint32_t tlas_root_is_leaf;  // a single instance
     uint32_t n_instances;
+    uint32_t leaf_vote; // lanes waiting at a leaf that end the node phase of the closest-hit walk (kernels.cu)
     uint32_t has_mesh; // any BLAS at all (a scene of spheres skips the cooperative leaf phase)
     uint32_t has_ext;  // any quad / cuboid / disk instance or sphere BLAS: selects the EXT traversal kernels
 };

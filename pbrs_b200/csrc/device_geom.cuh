@@ -183,6 +183,15 @@ PB_DEV bool mesh_tri_shade(const DeviceScene &sc, uint32_t tri_index, const TriV
     return true;
 }
 
+// The same as a real call: the closest-hit walk meets flagged triangles rarely, and its loop is
+// sensitive to every inlined instruction (registers, instruction cache).
+PB_CALL bool mesh_tri_shade_t(const DeviceScene &sc, uint32_t tri_index, const TriVerts &tv, const Ray &r, float &t, Diag &dg) {
+    MeshHit mh;
+    const bool hit = mesh_tri_shade(sc, tri_index, tv, r, mh, dg);
+    t = mh.t;
+    return hit;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Spheres.  shape/src/simple.rs:207-288.
 // ---------------------------------------------------------------------------------------------

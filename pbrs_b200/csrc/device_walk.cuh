@@ -116,8 +116,9 @@ PB_DEV int retest(float tl, float t_max) {
     return -1;
 }
 
-// EXT = the scene holds quads / cuboids / disks or a sphere BLAS (DeviceScene::has_ext); without
-// them the leaf code is the sphere + triangle-mesh code alone (3.5 % faster on the C4 workload).
+// EXT = the scene holds quads / cuboids / disks / isolated triangles, a sphere BLAS, or a triangle
+// whose hit the shading interpolation can reject (PBRS_TRI_CHECK_SHADING): DeviceScene::has_ext.
+// Without them the leaf code is the sphere + plain triangle code alone (3.5 % faster on C4).
 template <bool ANY, bool COUNT, bool EXT = true>
 struct Walk {
     // ray in the current space (world on the TLAS level, object inside a mesh instance)
@@ -275,10 +276,14 @@ struct Walk {
                     if (COUNT) tc.tris++;
                     float t;
                     bool hit;
-                    if (tv.flags & PBRS_TRI_CHECK_SHADING) {
+                    if (EXT && (tv.flags & PBRS_TRI_CHECK_SHADING)) {
+#if PBRS_TRISHADE_CALL
+                        hit = mesh_tri_shade_t(sc, s, tv, ray, t, dg);
+#else
                         MeshHit mh;
                         hit = mesh_tri_shade(sc, s, tv, ray, mh, dg);
                         t = mh.t;
+#endif
                     } else {
                         TriHit h;
                         hit = tri_intersect(tv.p0, tv.p1, tv.p2, ray, h, dg);

@@ -654,6 +654,8 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     ds.has_ext = s.simples.empty() ? 0u : 1u;
     for (const HostMesh &m : s.meshes)
         if (!m.balls.empty()) ds.has_ext = 1u;
+    for (const TriRec &t : f.tris)
+        if (t.flags & PBRS_TRI_CHECK_SHADING) { ds.has_ext = 1u; break; }
 }
 
 }  // namespace pbrs

@@ -185,6 +185,7 @@ PB_CALL bool simple_occludes(const SimpleRec *rec, uint32_t kind, const Ray &r, 
 }
 PB_CALL bool simple_intersect(const SimpleRec *rec, uint32_t kind, const Ray &r, Isect &out, Diag &dg) {
     const Simple s = load_simple(rec);
+    out.pos = r.o; out.t = 0.0f; out.u = out.v = 0.0f; out.normal = out.wo = -r.d; out.tangent = mk(1.0f, 0.0f, 0.0f);  // defined on a miss too
     if (kind == PBRS_SHAPE_QUAD) return quad_intersect(s.a, s.b, s.c, r, out, dg);
     if (kind == PBRS_SHAPE_CUBOID) return cuboid_intersect(s.a, s.b, r, out, dg);
     if (kind == PBRS_SHAPE_TRIANGLE) return isotri_shape_intersect(s.a, s.b, s.c, r, out, dg);

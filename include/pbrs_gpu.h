@@ -208,8 +208,7 @@ typedef struct pbrs_stats {
     uint64_t n_tris;        /* triangle records tested */
     uint64_t n_spheres;     /* sphere records tested */
     uint64_t n_instances;   /* instance leaves entered */
-    uint64_t would_panic[PBRS_NUM_PANIC_KINDS]; /* reference asserts that would have fired (evaluated on the
-                                                  * hits that win a walk, not on losing candidates) */
+    uint64_t would_panic[PBRS_NUM_PANIC_KINDS]; /* reference asserts that would have fired */
     double ms_total;        /* device time of the whole render call's GPU work */
     double ms_generate, ms_extend, ms_shade, ms_shadow, ms_accumulate; /* TIME_STAGES */
     uint64_t launches;      /* kernels launched by this call */

@@ -207,14 +207,23 @@ PB_DEV bool sphere_roots(vec3 c, float radius, const Ray &r, float &t0, float &t
     t1 = q / a;
     return true;
 }
-PB_DEV bool sphere_hit_t(vec3 c, float radius, const Ray &r, float &t) {
+// `far_root`: the hit is the far root, i.e. the ray leaves a sphere it started in.  The reference
+// builds the Interaction of every candidate and its normal.wo >= 0 assert fires there (D1) even when
+// the candidate then loses to a nearer hit; the walk records that with this flag instead of
+// normalising a normal per candidate (the winner gets the exact test in reconstruct_hit).
+PB_DEV bool sphere_hit_t(vec3 c, float radius, const Ray &r, float &t, bool &far_root) {
     float t0, t1;
+    far_root = false;
     if (!sphere_roots(c, radius, r, t0, t1)) return false;
     float t_low, t_high;
     if (t0 < t1) { t_low = t0; t_high = t1; } else { t_low = t1; t_high = t0; }
     if (in_extent(t_low, r.t_max)) { t = t_low; return true; }
-    if (in_extent(t_high, r.t_max)) { t = t_high; return true; }
+    if (in_extent(t_high, r.t_max)) { t = t_high; far_root = true; return true; }
     return false;
+}
+PB_DEV bool sphere_hit_t(vec3 c, float radius, const Ray &r, float &t) {
+    bool far_root;
+    return sphere_hit_t(c, radius, r, t, far_root);
 }
 // Q10: both roots must lie inside the extent (simple.rs:287)
 PB_DEV bool sphere_occludes(vec3 c, float radius, const Ray &r) {
@@ -223,9 +232,12 @@ PB_DEV bool sphere_occludes(vec3 c, float radius, const Ray &r) {
     return in_extent(t0, r.t_max) && in_extent(t1, r.t_max);
 }
 // One sphere of a sphere BLAS, out of line so the triangle-run loop only carries a call site.
-PB_CALL bool ball_test(vec3 c, float radius, const Ray &r, bool any, float &t) {
+PB_CALL bool ball_test(vec3 c, float radius, const Ray &r, bool any, float &t, Diag &dg) {
     if (any) return sphere_occludes(c, radius, r);
-    return sphere_hit_t(c, radius, r, t);
+    bool far_root;
+    const bool hit = sphere_hit_t(c, radius, r, t, far_root);
+    if (far_root) flag(dg, P_SPHERE_INSIDE);
+    return hit;
 }
 // The full Interaction of Sphere::intersect in the sphere's own space.  D1: a hit from
 // inside trips Interaction::new's assert upstream; flag it and face the normal to the ray.

@@ -265,7 +265,7 @@ struct Walk {
                     // IsoBlas<Sphere>: the leaf closure is the sphere's own test (blas.rs:267-274)
                     if (COUNT) tc.spheres++;
                     float t;
-                    if (ball_test(tv.p0, tv.p1.x, ray, ANY, t)) {
+                    if (ball_test(tv.p0, tv.p1.x, ray, ANY, t, dg)) {
                         if (ANY) { occluded = true; done = true; return; }
                         if (t < l_best_t) { l_best_t = t; l_best_tri = s; }
                     }
@@ -309,7 +309,9 @@ struct Walk {
             if (kind == PBRS_SHAPE_SPHERE) {
                 if (COUNT) tc.spheres++;
                 f4 s = ld16(sc.spheres + index);
-                hit = ANY ? sphere_occludes(mk(s.x, s.y, s.z), s.w, obj) : sphere_hit_t(mk(s.x, s.y, s.z), s.w, obj, t);
+                bool far_root = false;
+                hit = ANY ? sphere_occludes(mk(s.x, s.y, s.z), s.w, obj) : sphere_hit_t(mk(s.x, s.y, s.z), s.w, obj, t, far_root);
+                if (!ANY && far_root) flag(dg, P_SPHERE_INSIDE);
             } else if (!EXT) {
                 hit = false;  // unreachable: has_ext selects the EXT kernels
             } else {  // quad, cuboid, disk: shape/src/simple.rs

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 bool hit = false;
                 if (work) {
                     const TriVerts tv = load_tri(sc.tris + first + (e >> 5));
-                    if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { float t; hit = ball_test(tv.p0, tv.p1.x, r, true, t); }
+                    if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { float t; hit = ball_test(tv.p0, tv.p1.x, r, true, t, dg); }
                     else hit = tri_occludes(tv.p0, tv.p1, tv.p2, r, dg);
                 }
                 const unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);

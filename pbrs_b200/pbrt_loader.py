@@ -85,6 +85,25 @@ def tokenize(text, root_dir="."):
 
 
 # ---- FP32 matrices, math/src/hcm.rs (column vectors of a column-major Mat4) ----
+def _libm_f32(name):
+    """f32::sin / f32::cos are the platform libm's sinf / cosf (what the C++ loader calls too); numpy's
+    float32 kernels are a different implementation and differ from them in the last bit now and then."""
+    import ctypes
+    import ctypes.util
+    try:
+        fn = getattr(ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6"), name)
+        fn.restype = ctypes.c_float
+        fn.argtypes = [ctypes.c_float]
+        return lambda x: F32(fn(float(F32(x))))
+    except (OSError, AttributeError):
+        import math
+        ref = {"sinf": math.sin, "cosf": math.cos}[name]
+        return lambda x: F32(ref(float(F32(x))))   # correctly rounded double, rounded once more
+
+
+_sinf, _cosf = _libm_f32("sinf"), _libm_f32("cosf")
+
+
 def _ident():
     return np.eye(4, dtype=F32)
 
@@ -131,7 +150,7 @@ class Affine:
     @staticmethod
     def rotater(axis, angle_rad):  # transform.rs:146-152 over hcm.rs:508-520
         axis = np.asarray(axis, F32)
-        sin_t, cos_t = F32(np.sin(F32(angle_rad))), F32(np.cos(F32(angle_rad)))
+        sin_t, cos_t = _sinf(angle_rad), _cosf(angle_rad)
         f = _ident()
         dot = lambda a, b: F32(F32(a[0] * b[0] + a[1] * b[1]) + a[2] * b[2])
         ahat = axis * (F32(1.0) / F32(np.sqrt(dot(axis, axis))))

@@ -42,7 +42,31 @@ def transform(rng):
     return f"Scale {num(rng, 0.5, 1.6)} {num(rng, 0.5, 1.6)} {num(rng, 0.5, 1.6)}"
 
 
-def shape(rng):
+def ply_shape(rng, tmp, tag):
+    """A random binary PLY (either endianness, any index width, polygons, optional normals / uv)."""
+    from pbrs_b200.pbrt_loader import write_ply
+    nv = int(rng.integers(4, 12))
+    P = rng.uniform(-1.5, 1.5, (nv, 3)).astype(np.float32)
+    faces = []
+    for _ in range(int(rng.integers(1, 6))):
+        k = int(rng.integers(3, min(6, nv + 1)))
+        faces.append([int(v) for v in rng.choice(nv, size=k, replace=False)])
+    used = sorted({v for f in faces for v in f})
+    faces.append(list(range(nv))[:3])
+    for v in range(nv):   # every vertex in some face: compute_normals panics upstream otherwise
+        if v not in used:
+            faces.append([v, (v + 1) % nv, (v + 2) % nv])
+    N = rng.normal(size=(nv, 3)).astype(np.float32) if rng.random() < 0.4 else None
+    UV = rng.random((nv, 2)).astype(np.float32) if rng.random() < 0.5 else None
+    name = f"m{tag}.ply"
+    write_ply(os.path.join(tmp, name), P, None, N=N, UV=UV, big_endian=bool(rng.random() < 0.5),
+              index_type=str(rng.choice(["uchar", "short", "int", "uint"])), polygons=faces)
+    return f'Shape "plymesh" "string filename" "{name}"'
+
+
+def shape(rng, tmp=None, tag=0):
+    if tmp is not None and rng.random() < 0.25:
+        return ply_shape(rng, tmp, tag)
     if rng.random() < 0.5:
         return f'Shape "sphere" "float radius" [ {num(rng, 0.3, 1.0)} ]'
     n = int(rng.integers(1, 5))
@@ -54,13 +78,13 @@ def shape(rng):
     return f'Shape "trianglemesh" "point P" [ {P} ] "integer indices" [ {idx} ]{extra}'
 
 
-def block(rng, depth=0):
+def block(rng, depth=0, tmp=None):
     out = []
     for _ in range(int(rng.integers(1, 4))):
         r = rng.random()
         if r < 0.25 and depth < 3:
             kind = "Attribute" if rng.random() < 0.6 else "Transform"
-            inner = block(rng, depth + 1)
+            inner = block(rng, depth + 1, tmp)
             if kind == "Attribute": inner.insert(0, material(rng))
             out += [kind + "Begin"] + ["  " + l for l in inner] + [kind + "End"]
         elif r < 0.5:
@@ -68,11 +92,11 @@ def block(rng, depth=0):
         elif r < 0.6:
             out.append(material(rng))
         else:
-            out.append(shape(rng))
+            out.append(shape(rng, tmp, int(rng.integers(0, 1 << 30))))
     return out
 
 
-def scene_text(seed):
+def scene_text(seed, tmp=None):
     rng = np.random.default_rng(seed)
     lines = [f"LookAt {num(rng, -1, 1)} {num(rng, 0.5, 2.5)} -8  0 0.5 0  0 1 0",
              f'Camera "perspective" "float fov" [ {num(rng, 35, 65)} ]',
@@ -84,10 +108,11 @@ def scene_text(seed):
     if rng.random() < 0.5: lines.append(f'LightSource "infinite" "rgb L" [ {rgb(rng, 0.05, 0.4)} ]')
     lines.append(material(rng))
     lines.append('Shape "trianglemesh" "point P" [ -8 -1 -8  8 -1 -8  8 -1 8  -8 -1 8 ] "integer indices" [ 0 1 2 0 2 3 ]')
-    lines += block(rng)
+    lines += block(rng, 0, tmp)
     if rng.random() < 0.6:
+        lamp = ply_shape(rng, tmp, 999) if (tmp is not None and rng.random() < 0.4) else f'Shape "sphere" "float radius" [ {num(rng, 0.2, 0.7)} ]'
         lines += ["AttributeBegin", f'  AreaLightSource "diffuse" "rgb L" [ {rgb(rng, 5, 20)} ]', f"  Translate {num(rng, -2, 2)} 4 {num(rng, -2, 2)}",
-                  f'  Shape "sphere" "float radius" [ {num(rng, 0.2, 0.7)} ]', "AttributeEnd"]
+                  "  " + lamp, "AttributeEnd"]
     lines.append("WorldEnd")
     return "\n".join(lines) + "\n"
 
@@ -96,11 +121,11 @@ def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "hostsim"), "-s", "scene_file_check"])
     api = hs_load()
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
-    bad = 0
+    bad = loaded = 0
     tmp = tempfile.mkdtemp()
     for seed in range(lo, hi):
         path = os.path.join(tmp, f"s{seed}.pbrt")
-        open(path, "w").write(scene_text(seed))
+        open(path, "w").write(scene_text(seed, tmp))
         out = os.path.join(tmp, "ids.bin")
         r = subprocess.run([CHECK, path, out], capture_output=True, text=True)
         try:
@@ -115,6 +140,7 @@ def main():
             continue
         if not py_ok:
             continue
+        loaded += 1
         raw = np.fromfile(out, np.uint32)
         n = int(raw[0]) * int(raw[1])
         info = h.info()
@@ -125,7 +151,7 @@ def main():
         if not same:
             bad += 1
             print("FAIL", seed, "scene facts or ids differ", list(raw[:7]), flush=True)
-    print("done", lo, hi, "failures", bad)
+    print("done", lo, hi, "failures", bad, "| loaded by both", loaded, "refused by both", hi - lo - loaded - bad)
     return 1 if bad else 0
 
 

@@ -243,3 +243,29 @@ def test_bbox_slab_basic_and_nan_semantics(oracle_api):
     # t_max prunes
     out = O.kat(O.KAT_BBOX, [0, 0, 0, 1, 1, 1, -1, 0.5, 0.5, 1, 0, 0, 0.5], 2)[0]
     assert out[0] == 0.0
+
+
+def test_reference_transform_tests(oracle_api, hostsim_api):
+    """geometry/src/transform.rs:327-355 (`test_inverse`, `test_bbox_transform`) on the instance
+    transform both hosts use: rotater(axis (0.6, 0.8, 0), 0.3 rad) * translater; inverse * forward is
+    the identity to f32 epsilon, and the transformed box (what the TLAS leaf stores,
+    transform.rs:287-308) contains every transformed corner."""
+    from pbrs_b200.pbrt_loader import Affine, _mat_mul
+    from pbrs_b200.scene import SceneDesc
+    t = Affine.rotater((0.6, 0.8, 0.0), np.float32(0.3)) * Affine.translater((0.3, 0.4, 0.6))
+    ident = _mat_mul(t.inv, t.fwd)
+    assert ((ident[:3, :3] - np.eye(3, dtype=np.float32)) ** 2).sum() <= np.finfo(np.float32).eps
+    assert (ident[:3, 3] ** 2).sum() <= np.finfo(np.float32).eps
+    t = Affine.rotater((0.6, 0.8, 0.0), np.float32(0.3)) * Affine.translater((7.0, 8.0, -13.0))
+    lo, hi = np.array([-0.3, 0.4, 0.8], np.float32), np.array([3.4, 2.3, 4.4], np.float32)
+    for api in (oracle_api, hostsim_api):
+        sd = SceneDesc()
+        sd.set_camera(16, 16, 45.0, (0, 0, -30), (0, 0, 0))
+        sd.add_instance(sd.add_cuboid(tuple(lo), tuple(hi)), sd.lambertian((0.5, 0.5, 0.5)), fwd=t.fwd, inv=t.inv)
+        info = sd.realize(api).info()
+        wmin, wmax = np.array(info.world_min[:3], np.float32), np.array(info.world_max[:3], np.float32)
+        for cx in (lo[0], hi[0]):
+            for cy in (lo[1], hi[1]):
+                for cz in (lo[2], hi[2]):
+                    p = t.apply_point((cx, cy, cz))
+                    assert (p >= wmin).all() and (p <= wmax).all()

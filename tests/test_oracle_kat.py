@@ -269,3 +269,24 @@ def test_reference_transform_tests(oracle_api, hostsim_api):
                 for cz in (lo[2], hi[2]):
                     p = t.apply_point((cx, cy, cz))
                     assert (p >= wmin).all() and (p <= wmax).all()
+
+
+def test_reference_custom_frame_test(oracle_api):
+    """shape/tests/frame_test.rs:18-52: an Interaction with normal n and dpdu from
+    make_coord_system(n) keeps n and gets dpdu as its tangent.  Reached here through a quad whose
+    sides are (dpdu, dpdv): ParallelQuad::intersect ends in Interaction::new(.., n).with_dpdu(side_u)."""
+    from pbrs_b200.scene import SceneDesc
+    n = np.array([-0.3, 0.5, 1.0], F32); n = (n * (F32(1.0) / np.sqrt((n * n).sum(dtype=F32)))).astype(F32)
+    out, p = O.kat(O.KAT_MAKE_COORD, n, 6)
+    dpdu, dpdv = out[0:3].astype(F32), out[3:6].astype(F32)
+    assert p == 0 and abs(float(n @ dpdu)) < 1e-4 and abs(float(n @ dpdv)) < 1e-4
+    c = np.array([3.0, 2.5, 2.0], F32)
+    sd = SceneDesc()
+    sd.set_camera(16, 16, 45.0, (0, 0, -30), (0, 0, 0))
+    sd.add_instance(sd.add_quad(tuple(c - 0.5 * dpdu - 0.5 * dpdv), tuple(dpdu), tuple(dpdv)), sd.lambertian((0.5, 0.5, 0.5)))
+    h = sd.realize(oracle_api)
+    hit = O.trace_ray(h, tuple(c + 2.0 * n), tuple(-n))
+    assert hit[0] == 1.0 and hit[15] == 0.0                      # has_valid_frame: no assert fired
+    assert ((hit[12:15] - dpdu) ** 2).sum() < 1e-6               # tangent == dpdu
+    assert ((hit[5:8] - n) ** 2).sum() < 1e-6                    # normal == n (it already faces the ray)
+    np.testing.assert_allclose(hit[8:10], (0.5, 0.5), atol=1e-5)

@@ -565,71 +565,71 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     size_t ev_used = 0;
     // Everything the frame puts on the GPU, on `origin` (and, forked from it, the lane streams).
     auto enqueue = [&](cudaStream_t origin) -> int {
-    cudaStream_t stream = origin;
-    cudaStream_t const caller_stream = origin;
-    launches = launches_extend = launches_shadow = 0;
-    CK(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * kStatCount, stream));
-    if (n_batches) CK(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * PBRS_COUNTS_PER_BATCH * (size_t)n_batches, stream));
-    if (tg.film) CK(cudaMemsetAsync(tg.film, 0, sizeof(float) * 3 * (size_t)W * H, stream));
-    // PBRS_FLAG_TIME_STAGES: one event after every launch; stage time = sum of the gaps that end
-    // with a launch of that stage (the stream is in order, so a gap is that kernel's duration).
+        cudaStream_t stream = origin;
+        cudaStream_t const caller_stream = origin;
+        launches = launches_extend = launches_shadow = 0;
+        CK(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * kStatCount, stream));
+        if (n_batches) CK(cudaMemsetAsync(w.counts, 0, sizeof(uint32_t) * PBRS_COUNTS_PER_BATCH * (size_t)n_batches, stream));
+        if (tg.film) CK(cudaMemsetAsync(tg.film, 0, sizeof(float) * 3 * (size_t)W * H, stream));
+        // PBRS_FLAG_TIME_STAGES: one event after every launch; stage time = sum of the gaps that end
+        // with a launch of that stage (the stream is in order, so a gap is that kernel's duration).
 
-    auto mark = [&](int kind) -> int {
-        if (!time_stages) return 0;
-        if (ev_used == w.stage_ev.size()) {
-            cudaEvent_t e;
-            if (cudaEventCreate(&e) != cudaSuccess) return -1;
-            w.stage_ev.push_back(e);
+        auto mark = [&](int kind) -> int {
+            if (!time_stages) return 0;
+            if (ev_used == w.stage_ev.size()) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) return -1;
+                w.stage_ev.push_back(e);
+            }
+            cudaEventRecord(w.stage_ev[ev_used++], stream);
+            ev_kind.push_back(kind);
+            return 0;
+        };
+        mark(-1);
+        if (n_lanes > 1) {
+            CK(cudaEventRecord(w.fork_ev, caller_stream));
+            for (int l = 0; l < n_lanes; ++l) CK(cudaStreamWaitEvent(w.lane_stream[l], w.fork_ev, 0));
         }
-        cudaEventRecord(w.stage_ev[ev_used++], stream);
-        ev_kind.push_back(kind);
-        return 0;
-    };
-    mark(-1);
-    if (n_lanes > 1) {
-        CK(cudaEventRecord(w.fork_ev, caller_stream));
-        for (int l = 0; l < n_lanes; ++l) CK(cudaStreamWaitEvent(w.lane_stream[l], w.fork_ev, 0));
-    }
-    for (uint32_t b = 0; b < n_batches; ++b) {
-        PathBuffers pb = w.pb[b % (uint32_t)n_lanes];
-        stream = n_lanes > 1 ? w.lane_stream[b % (uint32_t)n_lanes] : caller_stream;
-        BatchParams bp;
-        bp.first_pixel = b * ppb;
-        bp.n_pixels = (uint32_t)std::min<uint64_t>(ppb, total_pixels - (uint64_t)b * ppb);
-        bp.n_paths = bp.n_pixels * fp.spp_r;
-        pb.counts = w.counts + (size_t)b * PBRS_COUNTS_PER_BATCH;
-        k_generate<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, pb.counts + PBRS_CNT_EXTEND);
-        ++launches;
-        mark(T_GEN);
-        for (int stage = 0; stage < n_stages; ++stage) {
-            uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
-            uint32_t *cnt = pb.counts + PBRS_CNT_STRIDE * stage, *next_cnt = cnt + PBRS_CNT_STRIDE;
-            if (count_trav) k_trace<false, true, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
-            else if (sc.has_ext) k_trace<false, false, true><<<w.grid.extend_ext, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
-            else k_trace<false, false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
-            ++launches; ++launches_extend;
-            mark(T_EXT);
-            if (tg.only_sample >= 0) break;
-            if (o.integrator == PBRS_INTEGRATOR_PATH) launch_shade<PBRS_INTEGRATOR_PATH>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
-            else launch_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
-            mark(T_SHADE);
-            if (count_trav) k_trace<true, true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
-            else if (sc.has_ext) k_trace<true, false, true><<<w.grid.shadow_ext, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
-            else k_trace<true, false, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
-            mark(T_SHADOW);
-            launches += PBRS_NUM_CLS + 1; ++launches_shadow;
-        }
-        if (tg.only_sample >= 0) {
-            k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
+        for (uint32_t b = 0; b < n_batches; ++b) {
+            PathBuffers pb = w.pb[b % (uint32_t)n_lanes];
+            stream = n_lanes > 1 ? w.lane_stream[b % (uint32_t)n_lanes] : caller_stream;
+            BatchParams bp;
+            bp.first_pixel = b * ppb;
+            bp.n_pixels = (uint32_t)std::min<uint64_t>(ppb, total_pixels - (uint64_t)b * ppb);
+            bp.n_paths = bp.n_pixels * fp.spp_r;
+            pb.counts = w.counts + (size_t)b * PBRS_COUNTS_PER_BATCH;
+            k_generate<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, pb.counts + PBRS_CNT_EXTEND);
             ++launches;
-        } else {
-            if (tg.film) { k_accumulate<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.film); ++launches; mark(T_ACC); }
-            if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; mark(T_ACC); }
+            mark(T_GEN);
+            for (int stage = 0; stage < n_stages; ++stage) {
+                uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
+                uint32_t *cnt = pb.counts + PBRS_CNT_STRIDE * stage, *next_cnt = cnt + PBRS_CNT_STRIDE;
+                if (count_trav) k_trace<false, true, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+                else if (sc.has_ext) k_trace<false, false, true><<<w.grid.extend_ext, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+                else k_trace<false, false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+                ++launches; ++launches_extend;
+                mark(T_EXT);
+                if (tg.only_sample >= 0) break;
+                if (o.integrator == PBRS_INTEGRATOR_PATH) launch_shade<PBRS_INTEGRATOR_PATH>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
+                else launch_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
+                mark(T_SHADE);
+                if (count_trav) k_trace<true, true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+                else if (sc.has_ext) k_trace<true, false, true><<<w.grid.shadow_ext, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+                else k_trace<true, false, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+                mark(T_SHADOW);
+                launches += PBRS_NUM_CLS + 1; ++launches_shadow;
+            }
+            if (tg.only_sample >= 0) {
+                k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
+                ++launches;
+            } else {
+                if (tg.film) { k_accumulate<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.film); ++launches; mark(T_ACC); }
+                if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; mark(T_ACC); }
+            }
         }
-    }
-    if (n_lanes > 1)
-        for (int l = 0; l < n_lanes; ++l) { CK(cudaEventRecord(w.join_ev[l], w.lane_stream[l])); CK(cudaStreamWaitEvent(caller_stream, w.join_ev[l], 0)); }
-    return 0;
+        if (n_lanes > 1)
+            for (int l = 0; l < n_lanes; ++l) { CK(cudaEventRecord(w.join_ev[l], w.lane_stream[l])); CK(cudaStreamWaitEvent(caller_stream, w.join_ev[l], 0)); }
+        return 0;
     };  // enqueue
 
     // a frame of a few batches is replayed from its graph; large frames (hundreds of batches of

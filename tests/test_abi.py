@@ -112,3 +112,13 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_ffi" not in text and "liboracle" not in text and "oracle/" not in text, os.path.join(dirpath, f)
                 assert "hostsim" not in text or f.endswith(".cuh"), os.path.join(dirpath, f)
+
+
+def test_integration_doc_binds_every_entry_point():
+    """INTEGRATION.md shows the Rust `extern "C"` item of every function include/pbrs_gpu.h declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "pbrs_gpu.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(pbrs_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (pbrs_[a-z0-9_]+)", open(os.path.join(root, "INTEGRATION.md")).read()))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))

@@ -85,9 +85,8 @@ struct TriHit {
     vec3 normal;          // unit geometric normal facing the ray
     vec3 pos;
 };
-PB_DEV bool tri_intersect(vec3 p0, vec3 p1, vec3 p2, const Ray &r, TriHit &h, Diag &dg) {
-    vec3 n;
-    if (!try_hat(cross(p0 - p1, p2 - p1), n)) return false;
+// intersect_triangle from the unit normal n = hat((p0 - p1) x (p2 - p1)) on (simple.rs:441-475)
+PB_DEV bool tri_intersect_n(vec3 p0, vec3 p1, vec3 p2, vec3 n, const Ray &r, TriHit &h, Diag &dg) {
     vec3 normal = facing(n, r.d);
     if (!(dot(normal, r.d) <= 0.0f)) flag(dg, P_MISC);
     float t = dot(normal, p0 - r.o) / dot(normal, r.d);
@@ -106,9 +105,13 @@ PB_DEV bool tri_intersect(vec3 p0, vec3 p1, vec3 p2, const Ray &r, TriHit &h, Di
     h.t = t; h.b0 = b0; h.b1 = b1; h.b2 = b2; h.normal = normal; h.pos = hp;
     return true;
 }
-PB_DEV bool tri_occludes(vec3 p0, vec3 p1, vec3 p2, const Ray &r, Diag &dg) {
-    vec3 normal;
-    if (!try_hat(cross(p0 - p1, p2 - p1), normal)) return false;
+PB_DEV bool tri_intersect(vec3 p0, vec3 p1, vec3 p2, const Ray &r, TriHit &h, Diag &dg) {
+    vec3 n;
+    if (!try_hat(cross(p0 - p1, p2 - p1), n)) return false;
+    return tri_intersect_n(p0, p1, p2, n, r, h, dg);
+}
+// intersect_triangle_pred from the unit normal on (simple.rs:481-495)
+PB_DEV bool tri_occludes_n(vec3 p0, vec3 p1, vec3 p2, vec3 normal, const Ray &r, Diag &dg) {
     float t = dot(normal, p0 - r.o) / dot(normal, r.d);
     if (!in_extent(t, r.t_max)) return false;
     vec3 p = at(r, t);
@@ -119,18 +122,70 @@ PB_DEV bool tri_occludes(vec3 p0, vec3 p1, vec3 p2, const Ray &r, Diag &dg) {
     bool g0 = b0 > 0.0f, g1 = b1 > 0.0f, g2 = b2 > 0.0f;
     return (g0 && g1 && g2) || (!g0 && !g1 && !g2);
 }
+PB_DEV bool tri_occludes(vec3 p0, vec3 p1, vec3 p2, const Ray &r, Diag &dg) {
+    vec3 normal;
+    if (!try_hat(cross(p0 - p1, p2 - p1), normal)) return false;
+    return tri_occludes_n(p0, p1, p2, normal, r, dg);
+}
 
+// A mesh triangle as it sits in HBM: the three positions and the precomputed unit normal
+// (records.h TriRec: bit-identical to what simple.rs:441 computes per test).
 struct TriVerts {
-    vec3 p0, p1, p2;
+    vec3 p0, p1, p2, n;
     uint32_t orig, flags;
 };
 PB_DEV TriVerts load_tri(const TriRec *t) {
-    f4 a = ld16(t), b = ld16(reinterpret_cast<const char *>(t) + 16), c = ld16(reinterpret_cast<const char *>(t) + 32);
+    const char *b = reinterpret_cast<const char *>(t);
+    f4 a = ld16(b), c = ld16(b + 16), d = ld16(b + 32), e = ld16(b + 48);
     TriVerts v;
     v.p0 = mk(a.x, a.y, a.z); v.orig = f2u(a.w);
-    v.p1 = mk(b.x, b.y, b.z); v.flags = f2u(b.w);
-    v.p2 = mk(c.x, c.y, c.z);
+    v.p1 = mk(c.x, c.y, c.z); v.flags = f2u(c.w);
+    v.p2 = mk(d.x, d.y, d.z);
+    v.n = mk(e.x, e.y, e.z);
     return v;
+}
+PB_DEV bool mesh_tri_intersect(const TriVerts &tv, const Ray &r, TriHit &h, Diag &dg) {
+    if (tv.flags & PBRS_TRI_DEGENERATE) return false;
+    return tri_intersect_n(tv.p0, tv.p1, tv.p2, tv.n, r, h, dg);
+}
+PB_DEV bool mesh_tri_occludes(const TriVerts &tv, const Ray &r, Diag &dg) {
+    if (tv.flags & PBRS_TRI_DEGENERATE) return false;
+    return tri_occludes_n(tv.p0, tv.p1, tv.p2, tv.n, r, dg);
+}
+// The rare tail of mesh_tri_hit_t: the hit position interpolated from the normalised barycentrics
+// must not be NaN (simple.rs:462-469).
+PB_CALL bool tri_hit_tail(vec3 p0, vec3 p1, vec3 p2, float b0, float b1, float total) {
+    b0 = b0 / total; b1 = b1 / total;
+    return !any_nan(bary_lerp(p0, p1, p2, b0, b1));
+}
+// What the closest-hit WALK needs of intersect_triangle: hit or not, and t.  Same decisions as
+// tri_intersect_n; the normalisation of the barycentrics and the interpolated position only feed
+// the final NaN rejection, which cannot fire when the barycentric sum is an ordinary number and
+// the vertices are moderate (all three terms have one sign, so |b_i / total| <= 1 + 3 ulp and
+// bary_lerp stays finite): then it is skipped, else evaluated out of line.
+PB_DEV bool mesh_tri_hit_t(const TriVerts &tv, const Ray &r, float &t_out, Diag &dg) {
+    if (tv.flags & PBRS_TRI_DEGENERATE) return false;
+    const float s = dot(tv.n, r.d);
+    const bool keep = sign_neg(s);            // facing(): n if n.d < 0, else -n
+    const vec3 normal = keep ? tv.n : -tv.n;
+    const float nd = dot(normal, r.d);
+    if (!(nd <= 0.0f)) flag(dg, P_MISC);
+    const float t = dot(normal, tv.p0 - r.o) / nd;
+    if (!in_extent(t, r.t_max)) return false;
+    const vec3 p = at(r, t);
+    const vec3 a = p - tv.p0, b = p - tv.p1, c = p - tv.p2;
+    const float b2 = dot(cross(a, b), normal);
+    const float b0 = dot(cross(b, c), normal);
+    const float b1 = dot(cross(c, a), normal);
+    if (is_nan(b0) || is_nan(b1) || is_nan(b2)) return false;
+    const bool g0 = b0 > 0.0f, g1 = b1 > 0.0f, g2 = b2 > 0.0f;
+    if (!((g0 && g1 && g2) || (!g0 && !g1 && !g2))) return false;
+    const float total = b0 + b1 + b2, mag = fabsf(total);
+    if (!(mag > 1e-30f && mag < 1e30f) || (tv.flags & PBRS_TRI_HUGE)) {
+        if (!tri_hit_tail(tv.p0, tv.p1, tv.p2, b0, b1, total)) return false;
+    }
+    t_out = t;
+    return true;
 }
 
 struct MeshHead {
@@ -158,7 +213,7 @@ struct MeshHit {
 PB_DEV bool mesh_tri_shade(const DeviceScene &sc, uint32_t tri_index, const TriVerts &tv, const Ray &r, MeshHit &out,
                            Diag &dg) {
     TriHit h;
-    if (!tri_intersect(tv.p0, tv.p1, tv.p2, r, h, dg)) return false;
+    if (!mesh_tri_intersect(tv, r, h, dg)) return false;
     float b0 = 1.0f - h.b1 - h.b2, b1 = h.b1, b2 = h.b2;
     vec3 hit_by_uv = tv.p0 + (tv.p1 - tv.p0) * b1 + (tv.p2 - tv.p0) * b2;
     if (!(len2(hit_by_uv - h.pos) < 1e-6f)) flag(dg, P_MESH_UV);

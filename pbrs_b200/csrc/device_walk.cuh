@@ -4,11 +4,18 @@
 // Why a state machine: in SIMT the naive nesting (TLAS loop -> instance -> BLAS loop -> leaf)
 // lets a lane that is deep inside a mesh run alone while its 31 neighbours wait at the TLAS
 // level (ncu on the first version: 7-11 of 32 lanes active, profiles/r1_v0_*).  Here every
-// lane, whatever level it is on, meets the others in the same two phases of `step()`:
+// lane, whatever level it is on, meets the others in the same two phases:
 //     phase 1  until the lane stands at a leaf: expand inner nodes (fetch the 64-byte record, test
 //              both child boxes, choose / push) and unwind the stack   (the hot loop, TLAS and BLAS alike)
 //     phase 2  one leaf: a triangle run, a sphere, or an instance entry
 // and the kernels (kernels.cu) refill finished lanes from the ray queue between steps.
+//
+// The whole state of a lane is the register `next`:
+//     >= 0           an inner node to expand          (link as loaded from the parent record)
+//     PBRS_NONE  -1  dead end: unwind the stack
+//     PBRS_DONE  -2  the walk is over (also: the lane is idle)
+//     <  -2          a leaf link (PBRS_LEAF_BIT | run length << 28 | first primitive)
+// so "advancing" and "at a leaf" are one signed compare each, and the warp's vote is two ballots.
 //
 // Exactness (DESIGN.md "Traversal"): the visit order, the extent each box/primitive is tested
 // against and every tie-break equal the reference's walks (tlas/src/bvh.rs:77-113,
@@ -23,14 +30,26 @@
 namespace pbrs {
 
 #define PBRS_NONE 0xFFFFFFFFu
+#define PBRS_DONE 0xFFFFFFFEu
 #define PBRS_TAG_COMBINE 0x40000000u  // TLAS closest: [lv] left value waiting for the right subtree's
-#define PBRS_TAG_EXIT 0x20000000u     // closest: boundary between the TLAS entries and a mesh walk's
-#define PBRS_WALK_STACK 160
+#define PBRS_TAG_EXIT 0x20000000u     // boundary between the TLAS entries and a mesh walk's
+// Stack entries alive at once: <= one per TLAS level (a pending right child or a COMBINE), the
+// EXIT tag, one far child per BLAS level; commit rejects scenes whose depths do not fit.
+#define PBRS_WALK_STACK 128
+#define PBRS_WALK_PARK 16  // words of world-ray state parked beside the stack during a mesh walk
 
-// relative margin of the pre-test: the product (mn - o) * fl(1/d) is within 1.5 * 2^-23 of the
-// quotient fl((mn - o) / d); 8 * 2^-23 leaves a 5x safety factor
+PB_DEV bool ref_advancing(uint32_t n) { return (int32_t)n >= -1; }
+PB_DEV bool ref_at_leaf(uint32_t n) { return (int32_t)n < -2; }
+
+// Relative margin of the pre-test.  With t = (mn - o) * fl(1/d) the product is within 2.5 ulp of the
+// reference's fl(fl(mn - o) / d); 16 * 2^-24 leaves a 3x safety factor.  PBRS_BOX_FMA evaluates
+// t = fma(mn, fl(1/d), fl(-o * fl(1/d))) instead: one instruction per slab instead of two, at the
+// price of an ABSOLUTE error of one ulp of |o / d|, which the per-ray constant `c0` covers.
 #define PBRS_BOX_MARGIN 9.5367431640625e-7f
 #define PBRS_BOX_TINY 1e-30f
+#ifndef PBRS_BOX_FMA
+#define PBRS_BOX_FMA 0
+#endif
 
 struct BoxTest {
     bool pass;     // t_low <= min(min_el, t_max): exactly the reference's outcome
@@ -50,8 +69,9 @@ PB_CALL BoxTest box_exact(float mnx, float mny, float mnz, float mxx, float mxy,
     return r;
 }
 
-// One child box against the ray.  `fast` = the ray's direction has no zero / non-finite
-// reciprocal, so the products below are finite or overflow to inf (never NaN).
+// One box against the ray (root boxes: once per walk / instance entry).  `fast` = the ray's
+// direction has no zero / non-finite reciprocal, so the products below are finite or overflow to
+// inf (never NaN).
 PB_DEV BoxTest test_box(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 o, vec3 d, vec3 rd, bool fast, float t_max) {
     BoxTest r;
     if (fast) {
@@ -73,123 +93,167 @@ PB_DEV BoxTest test_box(float mnx, float mny, float mnz, float mxx, float mxy, f
     }
     return box_exact(mnx, mny, mnz, mxx, mxy, mxz, o, d, t_max);
 }
+
 // Both child boxes of a node at once: one pre-test, one shared branch to the exact path.
+// A child's decision "t_low <= min(min_el, t_max)" is taken from the approximate values when the
+// difference of the two sides exceeds the error bound M * (|hi| + t_low) + c0 of that difference
+// (M = PBRS_BOX_MARGIN, c0 = the ray's absolute term), else from the exact divisions.
 // need_overlap: the caller also wants `overlap` of the right child (TLAS closest-hit only).
 struct PairTest {
-    BoxTest l, r;
+    bool lp, rp, rov;  // left / right pass, right overlap
+    float ltl, rtl;    // entry distances (approximate within the margin, or exact)
 };
-PB_DEV PairTest test_pair(f4 q0, f4 q1, f4 q2, vec3 o, vec3 d, vec3 rd, bool fast, float t_max, bool need_overlap) {
+PB_DEV PairTest test_pair(f4 q0, f4 q1, f4 q2, vec3 o, vec3 d, vec3 rd, vec3 nord, float c0, bool fast, float t_max, bool need_overlap) {
     PairTest p;
     if (fast) {
+#if PBRS_BOX_FMA
+        float ax = fmaf(q0.x, rd.x, nord.x), bx = fmaf(q0.w, rd.x, nord.x), cx = fmaf(q1.z, rd.x, nord.x), dx = fmaf(q2.y, rd.x, nord.x);
+        float ay = fmaf(q0.y, rd.y, nord.y), by = fmaf(q1.x, rd.y, nord.y), cy = fmaf(q1.w, rd.y, nord.y), dy = fmaf(q2.z, rd.y, nord.y);
+        float az = fmaf(q0.z, rd.z, nord.z), bz = fmaf(q1.y, rd.z, nord.z), cz = fmaf(q2.x, rd.z, nord.z), dz = fmaf(q2.w, rd.z, nord.z);
+#else
         float ax = (q0.x - o.x) * rd.x, bx = (q0.w - o.x) * rd.x, cx = (q1.z - o.x) * rd.x, dx = (q2.y - o.x) * rd.x;
         float ay = (q0.y - o.y) * rd.y, by = (q1.x - o.y) * rd.y, cy = (q1.w - o.y) * rd.y, dy = (q2.z - o.y) * rd.y;
         float az = (q0.z - o.z) * rd.z, bz = (q1.y - o.z) * rd.z, cz = (q2.x - o.z) * rd.z, dz = (q2.w - o.z) * rd.z;
+#endif
         float ltl = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), 0.0f);
         float lme = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
         float rtl = fmaxf(fmaxf(fmaxf(fminf(cx, dx), fminf(cy, dy)), fminf(cz, dz)), 0.0f);
         float rme = fminf(fminf(fmaxf(cx, dx), fmaxf(cy, dy)), fmaxf(cz, dz));
-        // margins (explicit fma: this is the approximate side, contraction is harmless here)
-        float lm = fmaf(PBRS_BOX_MARGIN, ltl, PBRS_BOX_TINY), ln = fmaf(PBRS_BOX_MARGIN, fabsf(lme), PBRS_BOX_TINY);
-        float rm = fmaf(PBRS_BOX_MARGIN, rtl, PBRS_BOX_TINY), rn = fmaf(PBRS_BOX_MARGIN, fabsf(rme), PBRS_BOX_TINY);
-        // pass = tl <= min(me, t_max): surely yes / surely no
-        bool l_yes = ltl + lm <= fminf(lme - ln, t_max), l_no = ltl - lm > fminf(lme + ln, t_max);
-        bool r_yes = rtl + rm <= fminf(rme - rn, t_max), r_no = rtl - rm > fminf(rme + rn, t_max);
-        bool sure = (l_yes || l_no) && (r_yes || r_no);  // false whenever a value is inf / NaN
-        bool r_ov_yes = rtl + rm <= rme - rn;
-        if (need_overlap) sure = sure && (r_ov_yes || rtl - rm > rme + rn);
-        if (sure) {
-            p.l.pass = l_yes; p.l.overlap = l_yes; p.l.tl = ltl;
-            p.r.pass = r_yes; p.r.overlap = r_ov_yes; p.r.tl = rtl;
-            return p;
+        // (explicit fma: this is the approximate side, contraction is harmless here)
+        const float lhi = fminf(lme, t_max), rhi = fminf(rme, t_max);
+        const float ldiff = lhi - ltl, rdiff = rhi - rtl;
+        const float lthr = fmaf(fabsf(lhi) + ltl, PBRS_BOX_MARGIN, c0), rthr = fmaf(fabsf(rhi) + rtl, PBRS_BOX_MARGIN, c0);
+        bool sure = fabsf(ldiff) > lthr && fabsf(rdiff) > rthr;  // false whenever a value is inf / NaN
+        p.lp = ldiff >= 0.0f; p.rp = rdiff >= 0.0f; p.rov = p.rp;
+        if (need_overlap) {
+            const float odiff = rme - rtl;
+            sure = sure && fabsf(odiff) > fmaf(fabsf(rme) + rtl, PBRS_BOX_MARGIN, c0);
+            p.rov = odiff >= 0.0f;
         }
+        if (sure) { p.ltl = ltl; p.rtl = rtl; return p; }
     }
-    p.l = box_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, t_max);
-    p.r = box_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, t_max);
+    const BoxTest l = box_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, t_max);
+    const BoxTest r = box_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, t_max);
+    p.lp = l.pass; p.rp = r.pass; p.rov = r.overlap; p.ltl = l.tl; p.rtl = r.tl;
     return p;
 }
 // Re-test of a stacked child against the extent of the moment (it overlapped when pushed):
 // pass iff t_low <= t_max.  Returns 1 pass, 0 fail, -1 too close to call with an approximate tl.
-PB_DEV int retest(float tl, float t_max) {
-    float m = PBRS_BOX_MARGIN * tl + PBRS_BOX_TINY;
+PB_DEV int retest(float tl, float t_max, float c0) {
+    float m = fmaf(PBRS_BOX_MARGIN, tl, c0);
     if (tl + m <= t_max) return 1;
     if (tl - m > t_max) return 0;
     return -1;
 }
 
+// The walk's stack in plain arrays (host build, sequential callers); the traversal kernels use a
+// shared-memory ring with the same interface (kernels.cu SmemStack).  Closest-hit entries are
+// (link, t_low) pairs, any-hit entries bare links; `park` is PBRS_WALK_PARK words beside the stack.
+template <bool ANY>
+struct ArrayStack {
+    uint32_t *ref;
+    float *tl;
+    uint32_t *park;
+    int sp;
+    PB_DEV ArrayStack(uint32_t *r, float *t, uint32_t *p) : ref(r), tl(t), park(p), sp(0) {}
+    PB_DEV void reset() { sp = 0; }
+    PB_DEV bool empty() const { return sp == 0; }
+    PB_DEV void push(uint32_t r, float t, Diag &dg) {
+        if (sp < PBRS_WALK_STACK) {
+            ref[sp] = r;
+            if (!ANY) tl[sp] = t;
+            ++sp;
+        } else {
+            flag(dg, P_STACK);
+        }
+    }
+    PB_DEV void pop(uint32_t &r, float &t) {
+        --sp;
+        r = ref[sp];
+        t = ANY ? 0.0f : tl[sp];
+    }
+    PB_DEV void park_set(int k, uint32_t v) { park[k] = v; }
+    PB_DEV uint32_t park_get(int k) const { return park[k]; }
+};
+
 // EXT = the scene holds quads / cuboids / disks / isolated triangles, a sphere BLAS, or a triangle
 // whose hit the shading interpolation can reject (PBRS_TRI_CHECK_SHADING): DeviceScene::has_ext.
 // Without them the leaf code is the sphere + plain triangle code alone (3.5 % faster on C4).
-template <bool ANY, bool COUNT, bool EXT = true>
+template <bool ANY, bool COUNT, bool EXT, class STK>
 struct Walk {
     // ray in the current space (world on the TLAS level, object inside a mesh instance)
     vec3 o, d, rd;
+#if PBRS_BOX_FMA
+    vec3 nord;  // fl(-o * rd)
+    float c0;   // absolute error term of the pre-test: 4 * 2^-24 * max |o * rd| + tiny
+#endif
     float t_max;
-    bool fast;
+    // bits 0..2: d.x / d.y / d.z > 0 (near-child choice, blas.rs:456); bit 3: `fast`; bit 4: inside a mesh
+    uint32_t bits;
     // (while a lane is inside a mesh instance its world ray, reciprocal direction and extent wait
-    // on the stack under the walk's entries -- see enter_mesh / leave_mesh -- not in registers)
-    uint32_t next;  // ref to visit (PBRS_LEAF_BIT = leaf), PBRS_NONE = unwind
-    uint32_t lvl;   // 0 = TLAS, 1 = inside a mesh instance
-    int sp;
-    bool done;
+    // in the park slots of the stack -- see enter / leave -- not in registers)
+    uint32_t next;
     // closest: running winner ("smallest t, right-most on ties"); any: occluded
     Hit best;
     bool occluded;
     // the mesh instance being walked
     float l_best_t;
     uint32_t l_best_tri, cur_inst;
-    uint32_t node_base, tri_base, mesh_index;  // of that mesh
-    float ret;  // TLAS closest: value of the subtree that just completed
-    // the stack lives in arrays owned by the caller (so that the scalars above stay in registers)
-    uint32_t *st_ref;
-    float *st_tl;
-    uint32_t *st_par;  // parent node (| side in bit 31) for the rare exact re-test
+    const NodeRec *nodes;  // node array of the current level (TLAS, or the mesh's first node)
+    uint32_t tri_base;     // of that mesh
+    float ret;             // TLAS closest: value of the subtree that just completed
+    STK st;
 
-    PB_DEV Walk(uint32_t *ref, float *tl, uint32_t *par) : st_ref(ref), st_tl(tl), st_par(par) {}
+    PB_DEV explicit Walk(const STK &s) : st(s) { next = PBRS_DONE; }
 
-    PB_DEV void set_space(vec3 no, vec3 nd, float nt) {
+    PB_DEV bool fast() const { return (bits & 8u) != 0u; }
+    PB_DEV bool in_mesh() const { return (bits & 16u) != 0u; }
+    PB_DEV bool done() const { return next == PBRS_DONE; }
+    PB_DEV bool at_leaf() const { return ref_at_leaf(next); }
+    PB_DEV bool advancing() const { return ref_advancing(next); }
+    PB_DEV float abs_term() const {
+#if PBRS_BOX_FMA
+        return c0;
+#else
+        return PBRS_BOX_TINY;
+#endif
+    }
+
+    PB_DEV void set_space(vec3 no, vec3 nd, float nt, uint32_t mesh_bit) {
         o = no; d = nd; t_max = nt;
         rd = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-        fast = is_fin(rd.x) && is_fin(rd.y) && is_fin(rd.z) && !any_nan(o);
+        const bool f = is_fin(rd.x) && is_fin(rd.y) && is_fin(rd.z) && !any_nan(o);
+        bits = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u) | (f ? 8u : 0u) | mesh_bit;
+#if PBRS_BOX_FMA
+        nord = mk(-(o.x * rd.x), -(o.y * rd.y), -(o.z * rd.z));
+        c0 = fmaf(fmaxf(fmaxf(fabsf(nord.x), fabsf(nord.y)), fabsf(nord.z)), 2.384185791015625e-7f, PBRS_BOX_TINY);
+#endif
     }
-    // Eleven words of world-ray state parked on the stack for the duration of a mesh walk.
-    PB_DEV void park(uint32_t a, uint32_t b, uint32_t c, Diag &dg) {
-        if (ANY) { push(a, 0.0f, 0u, dg); push(b, 0.0f, 0u, dg); push(c, 0.0f, 0u, dg); }
-        else push(a, u2f(b), c, dg);
-    }
-    PB_DEV void unpark(uint32_t &a, uint32_t &b, uint32_t &c) {
-        if (ANY) { c = st_ref[sp - 1]; b = st_ref[sp - 2]; a = st_ref[sp - 3]; sp -= 3; }
-        else { --sp; a = st_ref[sp]; b = f2u(st_tl[sp]); c = st_par[sp]; }
-    }
-    PB_DEV void save_world(Diag &dg) {
-        park(f2u(o.x), f2u(o.y), f2u(o.z), dg);
-        park(f2u(d.x), f2u(d.y), f2u(d.z), dg);
-        park(f2u(rd.x), f2u(rd.y), f2u(rd.z), dg);
-        park(f2u(t_max), fast ? 1u : 0u, cur_inst, dg);
-        if (!ANY) park(f2u(best.t), best.inst, best.tri, dg);
+    // World-ray state parked for the duration of a mesh walk (restored bit for bit; rd, bits and the
+    // FMA terms are recomputed from o and d by the same operations).
+    PB_DEV void save_world() {
+        st.park_set(0, f2u(o.x)); st.park_set(1, f2u(o.y)); st.park_set(2, f2u(o.z));
+        st.park_set(3, f2u(d.x)); st.park_set(4, f2u(d.y)); st.park_set(5, f2u(d.z));
+        st.park_set(6, f2u(t_max));
+        if (!ANY) { st.park_set(7, f2u(best.t)); st.park_set(8, best.inst); st.park_set(9, best.tri); st.park_set(10, cur_inst); }
     }
     PB_DEV void restore_world() {
-        uint32_t a, b, c;
-        if (!ANY) { unpark(a, b, c); best.t = u2f(a); best.inst = b; best.tri = c; }
-        unpark(a, b, c); t_max = u2f(a); fast = b != 0u; cur_inst = c;
-        unpark(a, b, c); rd = mk(u2f(a), u2f(b), u2f(c));
-        unpark(a, b, c); d = mk(u2f(a), u2f(b), u2f(c));
-        unpark(a, b, c); o = mk(u2f(a), u2f(b), u2f(c));
+        const vec3 wo = mk(u2f(st.park_get(0)), u2f(st.park_get(1)), u2f(st.park_get(2)));
+        const vec3 wd = mk(u2f(st.park_get(3)), u2f(st.park_get(4)), u2f(st.park_get(5)));
+        set_space(wo, wd, u2f(st.park_get(6)), 0u);
+        if (!ANY) { best.t = u2f(st.park_get(7)); best.inst = st.park_get(8); best.tri = st.park_get(9); cur_inst = st.park_get(10); }
     }
-    PB_DEV void push(uint32_t ref, float tl, uint32_t par, Diag &dg) {
-        if (sp < PBRS_WALK_STACK) {
-            st_ref[sp] = ref;
-            if (!ANY) { st_tl[sp] = tl; st_par[sp] = par; }  // any-hit entries are bare refs
-            ++sp;
+    // exact pass of the stacked child `ref` (the rare re-test): its box is in its parent's record
+    PB_DEV bool exact_child(const DeviceScene &sc, uint32_t ref, float extent) const {
+        uint32_t par;
+        const bool leaf = (ref & PBRS_LEAF_BIT) != 0u;
+        if (in_mesh()) {
+            const uint32_t node_base = (uint32_t)(nodes - sc.blas_nodes);
+            par = leaf ? ld_u32(sc.blas_leaf_parent + tri_base + (ref & PBRS_LEAF_FIRST_MASK)) : ld_u32(sc.blas_node_parent + node_base + ref);
         } else {
-            flag(dg, P_STACK);
+            par = leaf ? ld_u32(sc.tlas_leaf_parent + (ref & PBRS_LEAF_FIRST_MASK)) : ld_u32(sc.tlas_node_parent + ref);
         }
-    }
-    PB_DEV const NodeRec *node_ptr(const DeviceScene &sc, uint32_t idx) const {
-        return lvl ? sc.blas_nodes + node_base + idx : sc.tlas_nodes + idx;
-    }
-    // exact pass of child `side` of node `par` (the rare re-test)
-    PB_DEV bool exact_child(const DeviceScene &sc, uint32_t par, float extent) const {
-        const char *b = reinterpret_cast<const char *>(node_ptr(sc, par & 0x7FFFFFFFu));
+        const char *b = reinterpret_cast<const char *>(nodes + (par & 0x7FFFFFFFu));
         f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32);
         if (par & 0x80000000u) return box_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, d, extent).pass;
         return box_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, d, extent).pass;
@@ -197,57 +261,57 @@ struct Walk {
 
     // ---- start: the root box with the ray's own extent (tlas/src/bvh.rs:78,106) ----
     PB_DEV void begin(const DeviceScene &sc, const Ray &ray) {
-        set_space(ray.o, ray.d, ray.t_max);
-        lvl = 0u; sp = 0; done = false; occluded = false; ret = PB_INF;
+        set_space(ray.o, ray.d, ray.t_max, 0u);
+        st.reset();
+        occluded = false; ret = PB_INF;
         best.t = PB_INF; best.inst = PBRS_NONE; best.tri = PBRS_NONE;
-        BoxTest b = test_box(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], o, d, rd, fast, t_max);
-        if (!b.pass) { done = true; next = PBRS_NONE; return; }
+        nodes = sc.tlas_nodes;
+        BoxTest b = test_box(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], o, d, rd, fast(), t_max);
+        if (!b.pass) { next = PBRS_DONE; return; }
         next = sc.tlas_root_is_leaf ? PBRS_LEAF_BIT : 0u;
     }
 
-    PB_DEV bool at_leaf() const { return !done && next != PBRS_NONE && (next & PBRS_LEAF_BIT); }
     // phase 1: expansions and stack unwinds until the lane stands at a leaf (or is done)
-    PB_DEV bool advancing() const { return !done && !(next != PBRS_NONE && (next & PBRS_LEAF_BIT)); }
     PB_DEV void advance(const DeviceScene &sc, Diag &dg, TravCount &tc) {
         if (next != PBRS_NONE) expand(sc, dg, tc);
-        if (!done && next == PBRS_NONE) unwind(sc, dg);  // dead end: pop right away, same iteration
+        if (next == PBRS_NONE) unwind(sc, dg);  // dead end: pop right away, same iteration
     }
 
     // ---- phase 1: expand the inner node `next` ----
     PB_DEV void expand(const DeviceScene &sc, Diag &dg, TravCount &tc) {
         if (COUNT) tc.nodes++;
-        const uint32_t self = next;
-        const char *b = reinterpret_cast<const char *>(node_ptr(sc, self));
+        const char *b = reinterpret_cast<const char *>(nodes + next);
         f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32), q3 = ld16(b + 48);
-        const PairTest pt = test_pair(q0, q1, q2, o, d, rd, fast, t_max, !ANY && lvl == 0u);
-        const BoxTest &L = pt.l, &R = pt.r;
-        uint32_t meta = f2u(q3.z);
-        uint32_t lref = f2u(q3.x) | ((meta & PBRS_NODE_LEFT_LEAF) ? PBRS_LEAF_BIT : 0u);
-        uint32_t rref = f2u(q3.y) | ((meta & PBRS_NODE_RIGHT_LEAF) ? PBRS_LEAF_BIT : 0u);
+#if PBRS_BOX_FMA
+        const PairTest pt = test_pair(q0, q1, q2, o, d, rd, nord, c0, fast(), t_max, !ANY && !in_mesh());
+#else
+        const PairTest pt = test_pair(q0, q1, q2, o, d, rd, o, PBRS_BOX_TINY, fast(), t_max, !ANY && !in_mesh());
+#endif
+        const uint32_t lref = f2u(q3.x), rref = f2u(q3.y);  // leaf bit and run length are part of the link
         if (ANY) {
             // `left || right`, depth first (tlas/src/bvh.rs:105-113, blas.rs:478-495); the extent
             // never changes, so a pass is final.  (Visiting the nearer child first was measured:
             // 4 % MORE nodes on the C4 scene, so the reference's order stays.)
-            if (L.pass) {
-                if (R.pass) push(rref, 0.0f, 0u, dg);
+            if (pt.lp) {
+                if (pt.rp) st.push(rref, 0.0f, dg);
                 next = lref;
             } else {
-                next = R.pass ? rref : PBRS_NONE;
+                next = pt.rp ? rref : PBRS_NONE;
             }
             return;
         }
-        if (lvl) {
+        if (in_mesh()) {
             // shape/src/blas.rs:456-466: near = left iff dir[axis] > 0; the far child is pushed
             // first and re-tested against the extent of the moment when it is popped
-            bool left_near = comp(d, (int)(meta & 3u)) > 0.0f;
-            const BoxTest &N = left_near ? L : R, &F = left_near ? R : L;
-            if (F.pass) push(left_near ? rref : lref, F.tl, self | (left_near ? 0x80000000u : 0u), dg);
-            next = N.pass ? (left_near ? lref : rref) : PBRS_NONE;
+            const bool left_near = ((bits >> (f2u(q3.z) & 3u)) & 1u) != 0u;
+            const bool np = left_near ? pt.lp : pt.rp, fp = left_near ? pt.rp : pt.lp;
+            if (fp) st.push(left_near ? rref : lref, left_near ? pt.rtl : pt.ltl, dg);
+            next = np ? (left_near ? lref : rref) : PBRS_NONE;
             return;
         }
         // tlas/src/bvh.rs:83-100: left, then right against whatever extent the left subtree leaves
-        if (R.overlap) push(rref, R.tl, self | 0x80000000u, dg);
-        if (L.pass) next = lref;
+        if (pt.rov) st.push(rref, pt.rtl, dg);
+        if (pt.lp) next = lref;
         else { next = PBRS_NONE; ret = PB_INF; }
     }
 
@@ -255,7 +319,7 @@ struct Walk {
     PB_DEV void leaf(const DeviceScene &sc, Diag &dg, TravCount &tc) {
         const uint32_t first = next & PBRS_LEAF_FIRST_MASK;
         next = PBRS_NONE;
-        if (lvl) {
+        if (in_mesh()) {
             // a run of triangles (shape/src/blas.rs:447-454): all see the extent of the pop
             Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
             uint32_t s = tri_base + first;
@@ -266,29 +330,18 @@ struct Walk {
                     if (COUNT) tc.spheres++;
                     float t;
                     if (ball_test(tv.p0, tv.p1.x, ray, ANY, t, dg)) {
-                        if (ANY) { occluded = true; done = true; return; }
+                        if (ANY) { occluded = true; next = PBRS_DONE; return; }
                         if (t < l_best_t) { l_best_t = t; l_best_tri = s; }
                     }
                 } else if (ANY) {
                     if (COUNT) tc.tris++;
-                    if (tri_occludes(tv.p0, tv.p1, tv.p2, ray, dg)) { occluded = true; done = true; return; }
+                    if (mesh_tri_occludes(tv, ray, dg)) { occluded = true; next = PBRS_DONE; return; }
                 } else {
                     if (COUNT) tc.tris++;
                     float t;
                     bool hit;
-                    if (EXT && (tv.flags & PBRS_TRI_CHECK_SHADING)) {
-#if PBRS_TRISHADE_CALL
-                        hit = mesh_tri_shade_t(sc, s, tv, ray, t, dg);
-#else
-                        MeshHit mh;
-                        hit = mesh_tri_shade(sc, s, tv, ray, mh, dg);
-                        t = mh.t;
-#endif
-                    } else {
-                        TriHit h;
-                        hit = tri_intersect(tv.p0, tv.p1, tv.p2, ray, h, dg);
-                        t = h.t;
-                    }
+                    if (EXT && (tv.flags & PBRS_TRI_CHECK_SHADING)) hit = mesh_tri_shade_t(sc, s, tv, ray, t, dg);
+                    else hit = mesh_tri_hit_t(tv, ray, t, dg);
                     if (hit && t < l_best_t) { l_best_t = t; l_best_tri = s; }
                 }
                 if (tv.flags & PBRS_TRI_LAST_IN_LEAF) break;
@@ -319,7 +372,7 @@ struct Walk {
                 hit = ANY ? simple_occludes(sc.simples + index, kind, obj, dg) : simple_hit_t(sc.simples + index, kind, obj, t, dg);
             }
             if (ANY) {
-                if (hit) { occluded = true; done = true; }
+                if (hit) { occluded = true; next = PBRS_DONE; }
                 return;
             }
             if (hit) {
@@ -333,18 +386,17 @@ struct Walk {
         // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
         const MeshHead mesh = load_mesh_head(sc.meshes + index);
         cur_inst = first;
-        save_world(dg);
-        set_space(obj.o, obj.d, obj.t_max);
-        BoxTest rb = test_box(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], o, d, rd, fast, t_max);
+        save_world();
+        set_space(obj.o, obj.d, obj.t_max, 16u);
+        BoxTest rb = test_box(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], o, d, rd, fast(), t_max);
         if (!rb.pass) {
             restore_world();
             if (!ANY) ret = PB_INF;
             return;
         }
-        node_base = mesh.node_base; tri_base = mesh.tri_base; mesh_index = index;
+        nodes = sc.blas_nodes + mesh.node_base; tri_base = mesh.tri_base;
         l_best_t = PB_INF; l_best_tri = PBRS_NONE;
-        lvl = 1u;
-        push(PBRS_TAG_EXIT, 0.0f, 0u, dg);
+        st.push(PBRS_TAG_EXIT, 0.0f, dg);
         if (mesh.root_is_leaf) {
             next = PBRS_LEAF_BIT;  // its triangles see the incoming extent (the clone of `r`)
         } else {
@@ -356,14 +408,15 @@ struct Walk {
     // ---- phase 2b: unwind the stack until there is something to visit ----
     PB_DEV void unwind(const DeviceScene &sc, Diag &dg) {
         while (true) {
-            if (sp == 0) { done = true; return; }
-            --sp;
-            const uint32_t ref = st_ref[sp];
-            if (lvl) {
+            if (st.empty()) { next = PBRS_DONE; return; }
+            uint32_t ref;
+            float e_tl;
+            st.pop(ref, e_tl);
+            if (in_mesh()) {
                 if (ref == PBRS_TAG_EXIT) {
                     // the mesh walk is over: back to the world ray
-                    lvl = 0u;
                     restore_world();
+                    nodes = sc.tlas_nodes;
                     if (ANY) continue;
                     if (l_best_t < PB_INF) {
                         ret = l_best_t;
@@ -374,26 +427,23 @@ struct Walk {
                     continue;
                 }
                 if (ANY) { next = ref; return; }
-                int rt = retest(st_tl[sp], t_max);
-                if (rt < 0) rt = exact_child(sc, st_par[sp], t_max) ? 1 : 0;
+                int rt = retest(e_tl, t_max, abs_term());
+                if (rt < 0) rt = exact_child(sc, ref, t_max) ? 1 : 0;
                 if (rt) { next = ref; return; }
                 continue;
             }
             if (ANY) { next = ref; return; }
             if (ref == PBRS_TAG_COMBINE) {
-                float lv = st_tl[sp];
-                ret = (lv < ret) ? lv : ret;  // pick(l, r).t
+                ret = (e_tl < ret) ? e_tl : ret;  // pick(l, r).t
                 continue;
             }
             // a right child whose left sibling subtree just completed with value `ret`
-            const float r_tl = st_tl[sp];
-            const uint32_t par = st_par[sp];
             if (ret < PB_INF) {
                 t_max = ret;  // ray.set_extent(isect.ray_t), tlas/src/bvh.rs:85-87
-                st_ref[sp] = PBRS_TAG_COMBINE; st_tl[sp] = ret; ++sp;
+                st.push(PBRS_TAG_COMBINE, ret, dg);
             }
-            int rt = retest(r_tl, t_max);
-            if (rt < 0) rt = exact_child(sc, par, t_max) ? 1 : 0;
+            int rt = retest(e_tl, t_max, abs_term());
+            if (rt < 0) rt = exact_child(sc, ref, t_max) ? 1 : 0;
             if (rt) { next = ref; return; }
             ret = PB_INF;
         }
@@ -402,7 +452,7 @@ struct Walk {
     // the whole walk, sequentially (host-sim and single-ray callers)
     PB_DEV void run(const DeviceScene &sc, const Ray &ray, Diag &dg, TravCount &tc) {
         begin(sc, ray);
-        while (!done) {
+        while (!done()) {
             while (advancing()) advance(sc, dg, tc);
             if (at_leaf()) leaf(sc, dg, tc);
         }

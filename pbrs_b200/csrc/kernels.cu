@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "device_stages.cuh"
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 
 // Persistent traversal kernel (closest hit: ANY = false, shadow entries: ANY = true).
 // Every lane owns one Walk; the warp alternates phase 1 (inner-node expansions, all levels) and
-// phase 2 (one leaf or unwind) and, whenever enough lanes have run dry, draws the next rays from
-// the queue with a single atomicAdd on the launch's work cursor.
+// phase 2 (one leaf or unwind) and, whenever enough lanes have run dry, hands them the next rays
+// of the warp's chunk of the queue (one atomicAdd on the launch's work cursor per chunk).
 #ifndef PBRS_REFILL_IDLE_LANES
 #define PBRS_REFILL_IDLE_LANES 20
 #endif
@@ -100,14 +101,15 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 #endif
 // refill as soon as this many lanes are idle (closest-hit / any-hit walks tuned separately)
 template <bool ANY> constexpr int kRefillIdleLanes = ANY ? PBRS_REFILL_IDLE_LANES_ANY : PBRS_REFILL_IDLE_LANES;
-#ifndef PBRS_LEAF_VOTE
-#define PBRS_LEAF_VOTE 8
+#ifndef PBRS_REFILL_CHUNK
+#define PBRS_REFILL_CHUNK 64  // rays a warp draws from the queue per atomicAdd
 #endif
 #ifndef PBRS_LEAF_VOTE_ANY
 #define PBRS_LEAF_VOTE_ANY 12  // any-hit leaves are cheap to wait for: C5 shadow -7 %, C3/C4 unchanged (profiles/r1_exp_anyhit_vote.log)
 #endif
-// leave phase 1 once this many lanes wait at a leaf (32: all of them)
-template <bool ANY> constexpr int kLeafVote = ANY ? PBRS_LEAF_VOTE_ANY : PBRS_LEAF_VOTE;
+#ifndef PBRS_NODE_STEPS
+#define PBRS_NODE_STEPS 2  // node steps between two votes of the warp
+#endif
 
 // `cnt` = this stage's counter block (PBRS_CNT_*).
 #ifndef PBRS_TRACE_BLOCKS_PER_SM
@@ -116,6 +118,82 @@ template <bool ANY> constexpr int kLeafVote = ANY ? PBRS_LEAF_VOTE_ANY : PBRS_LE
 #ifndef PBRS_COOP_ANY
 #define PBRS_COOP_ANY 1
 #endif
+
+// The walk's stack on the device: a ring of the TOP entries per lane in shared memory (entry s of
+// lane l at ring[s * kThreads + l]: one bank per lane, so a push or pop is one conflict-free
+// wavefront whatever the lanes' stack depths are -- in local memory, lanes at different depths
+// touch different 128-byte lines), spilling its oldest entry to local memory when it is full and
+// reading back from there only after the ring has run empty.  Entries [lo, sp) are in the ring,
+// [0, lo) in local memory.  The parked world-ray state of a mesh walk sits in local memory at
+// fixed slots (all lanes the same address offset: coalesced).
+#ifndef PBRS_SMEM_STACK
+#define PBRS_SMEM_STACK 1
+#endif
+#ifndef PBRS_SMEM_STACK_CLOSEST
+#define PBRS_SMEM_STACK_CLOSEST 8   // (link, t_low) pairs: 8 KB per block of 128 threads
+#endif
+#ifndef PBRS_SMEM_STACK_ANY
+#define PBRS_SMEM_STACK_ANY 16      // bare links: 8 KB per block
+#endif
+template <bool ANY>
+struct SmemStack {
+    static constexpr int S = ANY ? PBRS_SMEM_STACK_ANY : PBRS_SMEM_STACK_CLOSEST;
+    static_assert((S & (S - 1)) == 0, "ring size must be a power of two");
+    using Entry = typename std::conditional<ANY, uint32_t, uint2>::type;
+    static constexpr uint32_t kSlotBytes = (uint32_t)sizeof(Entry) * kThreads;  // distance between two slots of a lane
+    uint32_t ring;        // shared-space byte address of this lane's slot 0
+    uint32_t *spill_ref;  // local memory, PBRS_WALK_STACK + PBRS_WALK_PARK words
+    float *spill_tl;
+    int sp, lo;
+    __device__ __forceinline__ SmemStack(Entry *r, uint32_t *sr, float *stl)
+        : ring((uint32_t)__cvta_generic_to_shared(r)), spill_ref(sr), spill_tl(stl), sp(0), lo(0) {}
+    __device__ __forceinline__ uint32_t slot(int i) const { return ring + ((uint32_t)i & (uint32_t)(S - 1)) * kSlotBytes; }
+    __device__ __forceinline__ void store(int i, uint32_t r, float t) {
+        if constexpr (ANY) asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot(i)), "r"(r) : "memory");
+        else asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot(i)), "r"(r), "r"(__float_as_uint(t)) : "memory");
+    }
+    __device__ __forceinline__ void load(int i, uint32_t &r, float &t) const {
+        if constexpr (ANY) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(slot(i)) : "memory");
+            t = 0.0f;
+        } else {
+            uint32_t tb;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r), "=r"(tb) : "r"(slot(i)) : "memory");
+            t = __uint_as_float(tb);
+        }
+    }
+    __device__ __forceinline__ void reset() { sp = 0; lo = 0; }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+    __device__ __forceinline__ void push(uint32_t r, float t, Diag &dg) {
+        if (sp - lo == S) {  // full: the oldest entry goes to local memory
+            if (lo < PBRS_WALK_STACK) {
+                uint32_t er; float et;
+                load(lo, er, et);
+                spill_ref[lo] = er;
+                if constexpr (!ANY) spill_tl[lo] = et;
+            } else {
+                flag(dg, P_STACK);
+            }
+            ++lo;
+        }
+        store(sp, r, t);
+        ++sp;
+    }
+    __device__ __forceinline__ void pop(uint32_t &r, float &t) {
+        --sp;
+        if (sp >= lo) {
+            load(sp, r, t);
+        } else {  // the ring ran empty: the entry is in local memory
+            const int k = sp < PBRS_WALK_STACK ? sp : PBRS_WALK_STACK - 1;
+            r = spill_ref[k];
+            t = ANY ? 0.0f : spill_tl[k];
+            lo = sp;
+        }
+    }
+    __device__ __forceinline__ void park_set(int k, uint32_t v) { spill_ref[PBRS_WALK_STACK + k] = v; }
+    __device__ __forceinline__ uint32_t park_get(int k) const { return spill_ref[PBRS_WALK_STACK + k]; }
+};
+
 template <bool ANY, bool COUNT, bool EXT>
 __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
     const uint32_t *count = cnt + (ANY ? PBRS_CNT_SHADOW : PBRS_CNT_EXTEND);
@@ -123,52 +201,71 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
     Diag dg; dg.panics = 0u;
     TravCount tc; tc.nodes = tc.tris = tc.spheres = tc.insts = 0u;
     const uint32_t n = *count;
-    uint32_t st_ref[PBRS_WALK_STACK], st_par[ANY ? 1 : PBRS_WALK_STACK];
+    // local memory: the spill area of the stack + the park slots (one array, dynamically indexed, so
+    // that the statically indexed park slots are not promoted to registers)
+    uint32_t st_ref[PBRS_WALK_STACK + PBRS_WALK_PARK];
     float st_tl[ANY ? 1 : PBRS_WALK_STACK];
-    Walk<ANY, COUNT, EXT> w(st_ref, st_tl, st_par);
-    w.done = true; w.next = PBRS_NONE;
+#if PBRS_SMEM_STACK
+    using Stk = SmemStack<ANY>;
+    __shared__ typename Stk::Entry ring_mem[Stk::S * kThreads];
+    Walk<ANY, COUNT, EXT, Stk> w(Stk(ring_mem + threadIdx.x, st_ref, st_tl));
+#else
+    using Stk = ArrayStack<ANY>;
+    Walk<ANY, COUNT, EXT, Stk> w(Stk(st_ref, st_tl, st_ref + PBRS_WALK_STACK));
+#endif
+    // the warp's chunk of the queue: [chunk[0], chunk[1]) is still to be handed out
+    __shared__ uint32_t chunk_mem[kThreads / 32][2];
+    uint32_t *chunk = chunk_mem[threadIdx.x >> 5];
+    if (lane_id() == 0u) { chunk[0] = 0u; chunk[1] = 0u; }
+    __syncwarp();
     bool busy = false, exhausted = false;
     uint32_t j = 0u, vis = 0u;
     int which = 0;
+    const int vote = ANY ? PBRS_LEAF_VOTE_ANY : (int)sc.leaf_vote;
     while (true) {
         // ---- refill idle lanes ----
-        unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
         if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= kRefillIdleLanes<ANY>)) {
-            int leader = __ffs(idle) - 1;
-            uint32_t base = 0u;
-            if ((int)lane_id() == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+            uint32_t c_next = chunk[0], c_end = chunk[1];
+            if (c_next == c_end) {
+                uint32_t base = 0u;
+                if (lane_id() == 0u) base = atomicAdd(cursor, (uint32_t)PBRS_REFILL_CHUNK);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base >= n) { exhausted = true; c_next = c_end = 0u; }
+                else { c_next = base; c_end = min(base + (uint32_t)PBRS_REFILL_CHUNK, n); }
+            }
+            const uint32_t take = min((uint32_t)__popc(idle), c_end - c_next);
             if (!busy) {
-                uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane_id()) - 1u));
-                if (i < n) {
-                    j = queue[i];
+                const uint32_t r = (uint32_t)__popc(idle & ((1u << lane_id()) - 1u));
+                if (r < take) {
+                    j = queue[c_next + r];
                     busy = true;
                     if (ANY) {
                         vis = 0u;
-                        Ray r;
+                        Ray ray;
                         which = 0;
-                        if (!shadow_ray(pb, j, 0, r)) { which = 1; shadow_ray(pb, j, 1, r); }
-                        w.begin(sc, r);
+                        if (!shadow_ray(pb, j, 0, ray)) { which = 1; shadow_ray(pb, j, 1, ray); }
+                        w.begin(sc, ray);
                     } else {
                         w.begin(sc, load_ray(pb, j));
                     }
                 }
             }
+            __syncwarp();
+            if (lane_id() == 0u) { chunk[0] = c_next + take; chunk[1] = c_end; }
+            __syncwarp();
         } else if (idle == 0xFFFFFFFFu) {
             break;
         }
-        // ---- phase 1: expansions / unwinds until every busy lane stands at a leaf or is done ----
-        if (kLeafVote<ANY> >= 32) {
-            while (busy && w.advancing()) w.advance(sc, dg, tc);
-        } else {
-            while (true) {
-                const bool adv = busy && w.advancing();
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, adv);
-                const unsigned waiting = __ballot_sync(0xFFFFFFFFu, busy && w.at_leaf());
-                if (m == 0u || __popc(waiting) >= (ANY ? kLeafVote<true> : (int)sc.leaf_vote)) break;
-                if (adv) w.advance(sc, dg, tc);
-            }
+        // ---- phase 1: expansions / unwinds until enough lanes stand at a leaf (or all are done) ----
+#pragma unroll 1
+        while (true) {
+            const unsigned m_adv = __ballot_sync(0xFFFFFFFFu, w.advancing());
+            const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, w.at_leaf());
+            if (m_adv == 0u || __popc(m_leaf) >= vote) break;
+#pragma unroll
+            for (int k = 0; k < PBRS_NODE_STEPS; ++k)
+                if (w.advancing()) w.advance(sc, dg, tc);
         }
         __syncwarp();
 #if PBRS_COOP_ANY
@@ -182,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
         if (ANY && !COUNT && sc.has_mesh) {
             __shared__ uint8_t coop_slots[kThreads];
             uint8_t *slot = coop_slots + (threadIdx.x & ~31u);
-            bool mine = busy && w.at_leaf() && w.lvl != 0u && ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) != 0u;
+            bool mine = w.at_leaf() && w.in_mesh() && ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) != 0u;
             unsigned owners = __ballot_sync(0xFFFFFFFFu, mine);
             while (owners) {
                 const uint32_t c = mine ? ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) : 0u;
@@ -210,12 +307,13 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 if (work) {
                     const TriVerts tv = load_tri(sc.tris + first + (e >> 5));
                     if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { float t; hit = ball_test(tv.p0, tv.p1.x, r, true, t, dg); }
-                    else hit = tri_occludes(tv.p0, tv.p1, tv.p2, r, dg);
+                    else hit = mesh_tri_occludes(tv, r, dg);
                 }
                 const unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
                 if (in_pass) {
-                    if (hits & (((1u << c) - 1u) << excl)) { w.occluded = true; w.done = true; }
-                    w.next = PBRS_NONE;  // the leaf is consumed; phase 1 unwinds from here
+                    // the leaf is consumed: occluded, or phase 1 unwinds from here
+                    if (hits & (((1u << c) - 1u) << excl)) { w.occluded = true; w.next = PBRS_DONE; }
+                    else w.next = PBRS_NONE;
                     mine = false;
                 }
                 __syncwarp();
@@ -224,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
         }
 #endif
         // ---- phase 2: one leaf ----
-        if (busy && w.at_leaf()) w.leaf(sc, dg, tc);
+        if (w.at_leaf()) w.leaf(sc, dg, tc);
         if (ANY) {
-            if (busy && w.done) {
+            if (busy && w.done()) {
                 if (!w.occluded) vis |= 1u << which;
                 Ray r;
                 if (which == 0 && shadow_ray(pb, j, 1, r)) {
@@ -240,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
         } else {
             // a finished walk: hit record out, path into the shade queue of its material class
             // (lanes of one class share one atomicAdd)
-            const bool fin = busy && w.done;
+            const bool fin = busy && w.done();
             const unsigned fmask = __ballot_sync(0xFFFFFFFFu, fin);
             if (fin) {
                 store_hit(pb, j, w.best);
@@ -391,6 +489,7 @@ struct Workspace {
     uint32_t counts_cap = 0;   // in batches
     uint32_t *tiles = nullptr;
     uint32_t tiles_cap = 0;
+    std::vector<uint32_t> tiles_host;  // what `tiles` holds
     unsigned long long *stats = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> stage_ev;  // PBRS_FLAG_TIME_STAGES: boundaries between launches
@@ -483,25 +582,54 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
         if (w.tiles) cudaFree(w.tiles);
         CK(cudaMalloc(&w.tiles, sizeof(uint32_t) * (size_t)n_tiles));
         w.tiles_cap = n_tiles;
+        w.tiles_host.clear();
     }
     for (auto &pb : w.pb) pb.stats = w.stats;
     return 0;
 }
 
-int check_last_frame(SceneImpl &s) {
-    if (!s.workspace || !s.workspace->stats) return 0;
+int check_last_frame(Replica &r) {
+    if (!r.workspace || !r.workspace->stats) return 0;
     unsigned long long overflow = 0;
-    CK(cudaMemcpy(&overflow, s.workspace->stats + kStatPanic0 + P_STACK, sizeof overflow, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&overflow, r.workspace->stats + kStatPanic0 + P_STACK, sizeof overflow, cudaMemcpyDeviceToHost));
     if (overflow) { set_error("a traversal stack overflowed (scene deeper than the commit-time bound allows?)"); return PBRS_ERR_UNSUPPORTED; }
     return 0;
 }
 
-int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st) {
+namespace {
+// the caller's current device, put back when the call returns
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
+// Tile t of the frame's 64x64 grid belongs to rank t % world_size (tile split), so every rank's
+// share is a regular lattice over the whole image; without a tile split a rank renders them all.
+void owned_tiles(const SceneImpl &s, const pbrs_render_opts &o, std::vector<uint32_t> &tiles) {
+    const uint32_t W = s.cam.width, H = s.cam.height;
+    uint32_t x0 = 0, y0 = 0, x1 = W, y1 = H;
+    if (o.crop_w != 0 && o.crop_h != 0) { x0 = o.crop_x; y0 = o.crop_y; x1 = o.crop_x + o.crop_w; y1 = o.crop_y + o.crop_h; }
+    const bool tile_split = o.world_size > 1 && o.split == PBRS_SPLIT_TILES;
+    const uint32_t tiles_x = (W + 63) / 64;
+    tiles.clear();
+    if (x1 <= x0 || y1 <= y0) return;
+    for (uint32_t ty = y0 / 64; ty <= (y1 - 1) / 64; ++ty)
+        for (uint32_t tx = x0 / 64; tx <= (x1 - 1) / 64; ++tx) {
+            uint32_t t = ty * tiles_x + tx;
+            if (tile_split && (t % (uint32_t)o.world_size) != (uint32_t)o.rank) continue;
+            tiles.push_back(t);
+        }
+}
+
+int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st) {
     if (!s.committed) { set_error("render before pbrs_scene_commit"); return PBRS_ERR_STATE; }
+    DeviceGuard device_guard;
     if (o.msaa == 0) { set_error("msaa must be >= 1"); return PBRS_ERR_INVALID_ARG; }
     if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) { set_error("bad rank/world_size"); return PBRS_ERR_INVALID_ARG; }
     if (o.integrator != PBRS_INTEGRATOR_PATH && o.integrator != PBRS_INTEGRATOR_DIRECT) { set_error("unknown integrator"); return PBRS_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(s.device));
+    CK(cudaSetDevice(r.device));
     const uint32_t W = s.cam.width, H = s.cam.height;
     FrameParams fp{};
     fp.seed = o.seed; fp.msaa = o.msaa; fp.spp = o.msaa * o.msaa;
@@ -518,15 +646,8 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     if (fp.only_sample >= 0) fp.spp_r = 1;
     else if (fp.split_samples) fp.spp_r = fp.spp > fp.rank ? (fp.spp - fp.rank + fp.world - 1) / fp.world : 0;
     else fp.spp_r = fp.spp;
-    const bool tile_split = o.world_size > 1 && o.split == PBRS_SPLIT_TILES;
-    const uint32_t tiles_x = (W + 63) / 64;
     std::vector<uint32_t> tiles;
-    for (uint32_t ty = fp.y0 / 64; ty <= (fp.y1 - 1) / 64; ++ty)
-        for (uint32_t tx = fp.x0 / 64; tx <= (fp.x1 - 1) / 64; ++tx) {
-            uint32_t t = ty * tiles_x + tx;
-            if (tile_split && (t % fp.world) != fp.rank) continue;
-            tiles.push_back(t);
-        }
+    owned_tiles(s, o, tiles);
     fp.n_tiles = (uint32_t)tiles.size();
 
     // stages per path: the path integrator's bounce loop, or the direct integrator's two stages
@@ -535,8 +656,10 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     if (n_stages > PBRS_MAX_STAGES) { set_error("max_depth too large (at most 15 bounces)"); return PBRS_ERR_INVALID_ARG; }
 
     // default 16 Mi paths (~4 GB of path state): measured +15 % over 4 Mi (fewer, longer launches; tails amortised)
-    uint32_t capacity = o.paths_in_flight ? o.paths_in_flight : (1u << 24);
+    // (a caller-supplied value is clamped from below: a tiny batch would mean millions of launches)
+    uint32_t capacity = o.paths_in_flight ? std::max(o.paths_in_flight, 1u << 16) : (1u << 24);
     const uint64_t total_pixels = (uint64_t)fp.n_tiles * 4096u;
+    if (total_pixels >> 32) { set_error("frame too large: more than 2^32 work pixels"); return PBRS_ERR_UNSUPPORTED; }
     const uint64_t total_paths = total_pixels * fp.spp_r;
     if (total_paths < capacity) capacity = (uint32_t)std::max<uint64_t>(total_paths, 32);
     if (capacity < fp.spp_r) capacity = fp.spp_r;
@@ -547,18 +670,24 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
     const bool want_stats = st != nullptr;
     // per-stage timing needs one in-order stream; everything else pipelines batches over two lanes
     const int n_lanes = (n_batches >= 2 && !(want_stats && (o.flags & PBRS_FLAG_TIME_STAGES))) ? PBRS_LANES : 1;
-    Workspace *&wp = s.workspace;
-    int rc = workspace_prepare(wp, s.device, capacity, n_lanes, std::max(n_batches, 1u), std::max(fp.n_tiles, 1u));
+    Workspace *&wp = r.workspace;
+    int rc = workspace_prepare(wp, r.device, capacity, n_lanes, std::max(n_batches, 1u), std::max(fp.n_tiles, 1u));
     if (rc < 0) return rc;
     Workspace &w = *wp;
     cudaStream_t const caller_stream = stream;
 
-    if (fp.n_tiles) CK(cudaMemcpyAsync(w.tiles, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, stream));
+    // the tile list is uploaded only when it differs from the one already on the device (a pageable
+    // source makes the copy synchronise with the host)
+    if (fp.n_tiles && tiles != w.tiles_host) {
+        CK(cudaMemcpyAsync(w.tiles, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));
+        w.tiles_host = tiles;
+    }
     fp.tiles = w.tiles;
     if (want_stats) CK(cudaEventRecord(w.ev[0], stream));
 
     uint64_t launches = 0, launches_extend = 0, launches_shadow = 0;
-    const DeviceScene &sc = s.dscene;
+    const DeviceScene &sc = r.dscene;
     const bool time_stages = want_stats && (o.flags & PBRS_FLAG_TIME_STAGES) != 0;
     std::vector<int> ev_kind;
     enum { T_GEN = 0, T_EXT = 1, T_SHADE = 2, T_SHADOW = 3, T_ACC = 4 };
@@ -594,7 +723,7 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
             PathBuffers pb = w.pb[b % (uint32_t)n_lanes];
             stream = n_lanes > 1 ? w.lane_stream[b % (uint32_t)n_lanes] : caller_stream;
             BatchParams bp;
-            bp.first_pixel = b * ppb;
+            bp.first_pixel = (uint32_t)((uint64_t)b * ppb);
             bp.n_pixels = (uint32_t)std::min<uint64_t>(ppb, total_pixels - (uint64_t)b * ppb);
             bp.n_paths = bp.n_pixels * fp.spp_r;
             pb.counts = w.counts + (size_t)b * PBRS_COUNTS_PER_BATCH;
@@ -648,7 +777,7 @@ int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &t
         fpk.tiles = fp.tiles; fpk.n_tiles = fp.n_tiles;
         put(shape, sizeof shape); put(&fpk, sizeof fpk); put(&total_pixels, sizeof total_pixels);
         const void *ptrs[12] = {tg.film, tg.samples, tg.ids_inst, tg.ids_prim, tg.ids_t, w.slab[0], w.slab[1], w.counts, w.stats, w.tiles,
-                                s.dscene.tlas_nodes, s.dscene.inst_trav};
+                                r.dscene.tlas_nodes, r.dscene.inst_trav};
         put(ptrs, sizeof ptrs);
         if (!w.graph_exec || key != w.graph_key) {
             if (w.graph_exec) { cudaGraphExecDestroy(w.graph_exec); w.graph_exec = nullptr; }

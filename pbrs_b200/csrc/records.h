@@ -3,7 +3,8 @@
 //
 // Sizes are the ones SURVEY.md 8(d) prices a ray with:
 //   inner node   64 B  (both children's boxes + links: one fetch per expansion)
-//   triangle     48 B  (3 x float4 positions, ids in the pad lanes)
+//   triangle     48 B  (3 x float4 positions, ids in the pad lanes) + 16 B: the unit geometric normal
+//                      every test of the triangle starts from (precomputed at commit, see TriRec)
 //   sphere       16 B  (centre + radius)
 //   instance    128 B  (64 B traversal half: inverse 3x4 + shape link;
 //                       64 B shading half: forward 3x4 + material link)
@@ -16,10 +17,11 @@ namespace pbrs {
 //   bits 0..1   split axis (BLAS only; tlas/src/bvh.rs keeps no axis)
 //   bit  2      left child is a leaf      bit 3  right child is a leaf
 //   bits 4..17  left leaf primitive count  bits 18..31 right leaf primitive count (informative)
-// For a leaf child, child[k] = first primitive (BLAS: index into the mesh's triangle
-// records, relative to the mesh's first record; the leaf runs up to and including the first
-// record carrying PBRS_TRI_LAST_IN_LEAF.  TLAS: instance id).  For an inner child,
-// child[k] = node index (BLAS: relative to the mesh's first node).
+// For a leaf child, child[k] = PBRS_LEAF_BIT | first primitive (BLAS: index into the mesh's
+// triangle records, relative to the mesh's first record; the leaf runs up to and including the
+// first record carrying PBRS_TRI_LAST_IN_LEAF.  TLAS: instance id).  For an inner child,
+// child[k] = node index (BLAS: relative to the mesh's first node).  The leaf bit is baked into the
+// link at commit so that the walk's `next` register is the link as loaded.
 struct NodeRec {
     float lmin[3], lmax[3];
     float rmin[3], rmax[3];
@@ -42,6 +44,11 @@ static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
 
 // p0/p1/p2 already carry the reference's (i, k, j) vertex swap (shape/src/blas.rs:162-163):
 // p0 = pos[idx.0], p1 = pos[idx.2], p2 = pos[idx.1].
+// n = hat((p0 - p1) x (p2 - p1)): the unit normal shape/src/simple.rs:441,481 recompute for every
+// test.  It depends on the triangle alone, so commit evaluates it once with the same IEEE FP32
+// operations (scene_host.cpp, -ffp-contract=off) and the tests start from it: bit-identical, and
+// a cross product, a square root and a division fewer per test.  A triangle whose normal cannot
+// be normalised (try_hat fails: the reference returns None) carries PBRS_TRI_DEGENERATE.
 struct TriRec {
     float p0[3];
     uint32_t orig;   // triangle index in the caller's idx array (the primitive id)
@@ -49,14 +56,20 @@ struct TriRec {
     uint32_t flags;  // PBRS_TRI_*
     float p2[3];
     uint32_t pad;
+    float n[3];
+    uint32_t pad2;
 };
-static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+static_assert(sizeof(TriRec) == 64, "TriRec must be 64 bytes");
 // The hit can be rejected by TriangleMesh::intersect_triangle's tangent check
 // (shape/src/blas.rs:193-201); the traversal must evaluate the shading interpolation for it.
 #define PBRS_TRI_CHECK_SHADING 1u
 #define PBRS_TRI_LAST_IN_LEAF 2u
 // The record is a sphere of an IsoBlas<Sphere> (shape/src/blas.rs:36-70): p0 = centre, p1[0] = radius.
 #define PBRS_TRI_SPHERE 4u
+#define PBRS_TRI_DEGENERATE 8u   // try_hat of the geometric normal fails: every test misses
+// A vertex coordinate beyond 1e18 in magnitude: the walk's shortcut for the "interpolated hit
+// position is NaN" rejection (simple.rs:467-469) is not provably safe, the full test runs instead.
+#define PBRS_TRI_HUGE 16u
 
 // Shading attributes of one triangle, gathered per TRIANGLE (same index as its TriRec) instead of
 // per vertex: one dependent fetch after the hit record instead of three (index triple, then the
@@ -199,6 +212,12 @@ struct DeviceScene {
     const InstShadeRec *inst_shade;
     const MeshRec *meshes;
     const TriShadeRec *tri_shade;  // per triangle, same index as `tris`
+    // Parent links, read only by the rare exact re-test of a stacked child (device_walk.cuh):
+    // node (| bit 31 = the child is the right one) whose record holds the child's box.
+    const uint32_t *blas_node_parent;  // per BLAS inner node (same index as blas_nodes)
+    const uint32_t *blas_leaf_parent;  // per triangle record: valid at the first record of a leaf
+    const uint32_t *tlas_node_parent;  // per TLAS inner node
+    const uint32_t *tlas_leaf_parent;  // per instance
     const MaterialRec *materials;
     const TextureRec *textures;
     const uint32_t *texels;     // RGBA8

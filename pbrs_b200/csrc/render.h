@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "scene_host.h"
 
 namespace pbrs {
@@ -20,10 +22,14 @@ struct Workspace;  // path buffers, queues and counters kept between calls (kern
 void workspace_free(Workspace *);
 
 // Enqueues the whole frame on `stream`; synchronises only when `st` is given.
-int render_frame(SceneImpl &s, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st);
+// One frame is in flight per replica at a time: the path workspace, counters and the cached graph
+// belong to the replica.  The caller's current device is restored on return.
+int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, const RenderTargets &tg, cudaStream_t stream, pbrs_stats *st);
+// The 64x64 tiles of the render region that `rank` of `world` owns (tile split), in render order.
+void owned_tiles(const SceneImpl &s, const pbrs_render_opts &o, std::vector<uint32_t> &tiles);
 
 // After the frame's work has completed on the host side (the caller synchronised): fails loudly
 // if a traversal stack overflowed during the last render_frame on this scene.
-int check_last_frame(SceneImpl &s);
+int check_last_frame(Replica &r);
 
 }  // namespace pbrs

@@ -40,33 +40,32 @@ int upload(DeviceArrays &d, const std::vector<T> &v, const T *&out) {
 
 }  // namespace
 
-void device_free(SceneImpl &s) {
-    if (s.workspace) { workspace_free(s.workspace); s.workspace = nullptr; }
-    if (s.film) { cudaFree(s.film); s.film = nullptr; s.film_bytes = 0; }
-    if (!s.dev) return;
-    for (void *p : s.dev->allocs) cudaFree(p);
-    delete s.dev;
-    s.dev = nullptr;
+static void replica_free(Replica &r) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (r.device >= 0) cudaSetDevice(r.device);
+    if (r.workspace) { workspace_free(r.workspace); r.workspace = nullptr; }
+    if (r.film) { cudaFree(r.film); r.film = nullptr; r.film_bytes = 0; }
+    if (r.dev) {
+        for (void *p : r.dev->allocs) cudaFree(p);
+        delete r.dev;
+        r.dev = nullptr;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
-int device_upload(SceneImpl &s) {
-    int n_dev = 0;
-    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
-        cudaGetLastError();
-        set_error("no usable CUDA device (this back end has no CPU fallback)");
-        return PBRS_ERR_NO_DEVICE;
-    }
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return PBRS_ERR_NO_DEVICE; }
-    s.device = dev;
-    device_free(s);
-    s.dev = new DeviceArrays();
-    DeviceArrays &d = *s.dev;
-    DeviceScene &ds = s.dscene;
-    std::memset(&ds, 0, sizeof ds);
+void device_free(SceneImpl &s) {
+    replica_free(s);
+    for (Replica *r : s.extra) { replica_free(*r); delete r; }
+    s.extra.clear();
+}
 
-    FlatScene f;
-    flatten_scene(s, f);
+// Uploads the flattened records to the CURRENT device and points r.dscene at them.
+static int upload_records(const SceneImpl &s, const FlatScene &f, Replica &r) {
+    r.dev = new DeviceArrays();
+    DeviceArrays &d = *r.dev;
+    DeviceScene &ds = r.dscene;
+    std::memset(&ds, 0, sizeof ds);
     int rc = 0;
     if ((rc = upload(d, s.tlas_nodes, ds.tlas_nodes)) < 0) return rc;
     if ((rc = upload(d, f.blas_nodes, ds.blas_nodes)) < 0) return rc;
@@ -84,10 +83,44 @@ int device_upload(SceneImpl &s) {
     if ((rc = upload(d, f.perlin_perm, ds.perlin_perm)) < 0) return rc;
     if ((rc = upload(d, s.delta_lights, ds.delta_lights)) < 0) return rc;
     if ((rc = upload(d, s.area_lights, ds.area_lights)) < 0) return rc;
-
+    if ((rc = upload(d, f.blas_node_parent, ds.blas_node_parent)) < 0) return rc;
+    if ((rc = upload(d, f.blas_leaf_parent, ds.blas_leaf_parent)) < 0) return rc;
+    if ((rc = upload(d, f.tlas_node_parent, ds.tlas_node_parent)) < 0) return rc;
+    if ((rc = upload(d, f.tlas_leaf_parent, ds.tlas_leaf_parent)) < 0) return rc;
     fill_scene_constants(s, f, ds);
-    s.info.device_bytes = d.bytes;
     return 0;
+}
+
+int device_upload(SceneImpl &s) {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        set_error("no usable CUDA device (this back end has no CPU fallback)");
+        return PBRS_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return PBRS_ERR_NO_DEVICE; }
+    device_free(s);
+    s.device = dev;
+    FlatScene f;
+    flatten_scene(s, f);
+    int rc = upload_records(s, f, s);
+    if (rc < 0) return rc;
+    s.info.device_bytes = s.dev->bytes;
+    return 0;
+}
+
+// A further copy of the committed scene on `device` (pbrs_render with num_gpus > 1).
+int device_upload_replica(const SceneImpl &s, Replica &r, int device) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("replicate: cudaSetDevice failed"); return PBRS_ERR_NO_DEVICE; }
+    r.device = device;
+    FlatScene f;
+    flatten_scene(s, f);
+    int rc = upload_records(s, f, r);
+    cudaSetDevice(prev);
+    return rc;
 }
 
 }  // namespace pbrs

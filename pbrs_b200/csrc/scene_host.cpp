@@ -59,6 +59,8 @@ inline int widest_axis(float x, float y, float z) {  // Vec3::max_dimension, mat
     return z > rv ? 2 : r;
 }
 
+constexpr uint32_t PBRS_LEAF_LINK = 0x80000000u;  // == PBRS_LEAF_BIT of the device headers
+
 struct ChildLink {
     bool leaf;
     uint32_t ref;    // node index or first primitive
@@ -69,7 +71,7 @@ struct ChildLink {
 void write_child(NodeRec &n, int side, const ChildLink &c) {
     float *mn = side == 0 ? n.lmin : n.rmin, *mx = side == 0 ? n.lmax : n.rmax;
     for (int k = 0; k < 3; ++k) { mn[k] = c.box.mn[k]; mx[k] = c.box.mx[k]; }
-    n.child[side] = c.ref;
+    n.child[side] = c.leaf ? (c.ref | PBRS_LEAF_LINK) : c.ref;
     if (c.leaf) {
         n.meta |= side == 0 ? PBRS_NODE_LEFT_LEAF : PBRS_NODE_RIGHT_LEAF;
         n.meta |= (c.count & 0x3FFFu) << (side == 0 ? 4 : 18);
@@ -573,7 +575,22 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
             for (int c = 0; c < 3; ++c) { tr.p0[c] = m.P[3 * i + c]; tr.p1[c] = m.P[3 * j + c]; tr.p2[c] = m.P[3 * k + c]; }
             tr.orig = t;
             tr.flags = host_tri_may_reject(m, t) ? PBRS_TRI_CHECK_SHADING : 0u;
-            tr.pad = 0u;
+            tr.pad = 0u; tr.pad2 = 0u;
+            {   // n = try_hat((p0 - p1) x (p2 - p1)), shape/src/simple.rs:441,481 over math/src/hcm.rs:118-121
+                float e0[3], e1[3], cr[3];
+                v_sub(tr.p0, tr.p1, e0);
+                v_sub(tr.p2, tr.p1, e1);
+                v_cross(e0, e1, cr);
+                const float inv = 1.0f / std::sqrt(v_dot(cr, cr));
+                if (std::isfinite(inv) && inv != 0.0f) {
+                    for (int c = 0; c < 3; ++c) tr.n[c] = inv * cr[c];
+                } else {
+                    for (int c = 0; c < 3; ++c) tr.n[c] = 0.0f;
+                    tr.flags |= PBRS_TRI_DEGENERATE;
+                }
+                for (int c = 0; c < 3; ++c)
+                    if (!(std::fabs(tr.p0[c]) < 1e18f && std::fabs(tr.p1[c]) < 1e18f && std::fabs(tr.p2[c]) < 1e18f)) tr.flags |= PBRS_TRI_HUGE;
+            }
             TriShadeRec &sr = tri_shade[t0 + q];
             const uint32_t v3[3] = {i, j, k};
             float *nd[3] = {sr.n0, sr.n1, sr.n2}, *ud[3] = {sr.uv0, sr.uv1, sr.uv2};
@@ -584,7 +601,24 @@ void flatten_scene(const SceneImpl &s, FlatScene &f) {
             sr.pad = 0.0f;
         }
         for (uint32_t last : m.leaf_last) tris[t0 + last].flags |= PBRS_TRI_LAST_IN_LEAF;
+        // parent links of this mesh's nodes and leaves (for the exact re-test of a stacked child)
+        f.blas_node_parent.resize(blas_nodes.size(), 0u);
+        f.blas_leaf_parent.resize(tris.size(), 0u);
+        for (size_t p = 0; p < m.nodes.size(); ++p)
+            for (uint32_t side = 0; side < 2; ++side) {
+                const uint32_t link = m.nodes[p].child[side], tag = (uint32_t)p | (side << 31);
+                if (link & PBRS_LEAF_LINK) f.blas_leaf_parent[t0 + (link & PBRS_LEAF_FIRST_MASK)] = tag;
+                else f.blas_node_parent[r.node_base + link] = tag;
+            }
     }
+    f.tlas_node_parent.assign(s.tlas_nodes.size(), 0u);
+    f.tlas_leaf_parent.assign(s.instances.size(), 0u);
+    for (size_t p = 0; p < s.tlas_nodes.size(); ++p)
+        for (uint32_t side = 0; side < 2; ++side) {
+            const uint32_t link = s.tlas_nodes[p].child[side], tag = (uint32_t)p | (side << 31);
+            if (link & PBRS_LEAF_LINK) f.tlas_leaf_parent[link & PBRS_LEAF_FIRST_MASK] = tag;
+            else f.tlas_node_parent[link] = tag;
+        }
 
     // ---- instances ----
     trav.assign(s.instances.size(), InstTravRec{});

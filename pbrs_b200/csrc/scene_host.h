@@ -50,7 +50,19 @@ struct HostTexture {
 struct DeviceArrays;  // opaque (scene_device.cu)
 struct Workspace;     // opaque (kernels.cu)
 
-struct SceneImpl {
+// Everything a scene owns on ONE device: the uploaded records, the path workspace, the device film.
+// The scene itself is replica 0 (the device that was current at pbrs_scene_commit); a render with
+// num_gpus > 1 adds one replica per further device (api_render.cu).
+struct Replica {
+    DeviceArrays *dev = nullptr;
+    Workspace *workspace = nullptr;
+    float *film = nullptr;         // device film of pbrs_render, kept between calls
+    size_t film_bytes = 0;
+    DeviceScene dscene{};
+    int device = -1;
+};
+
+struct SceneImpl : Replica {
     bool has_camera = false, committed = false;
     CameraRec cam{};
     std::vector<HostTexture> textures;
@@ -73,12 +85,7 @@ struct SceneImpl {
     uint32_t tlas_depth = 0;
     pbrs_scene_info info{};
 
-    DeviceArrays *dev = nullptr;
-    Workspace *workspace = nullptr;
-    float *film = nullptr;         // device film of pbrs_render, kept between calls
-    size_t film_bytes = 0;
-    DeviceScene dscene{};
-    int device = -1;
+    std::vector<Replica *> extra;  // replicas on further devices (num_gpus > 1), in device order
 };
 
 // The flattened record arrays (host copies; scene_device.cu uploads them verbatim).
@@ -91,6 +98,7 @@ struct FlatScene {
     std::vector<InstShadeRec> shade;
     std::vector<TextureRec> textures;
     std::vector<uint32_t> texels, perlin_perm;
+    std::vector<uint32_t> blas_node_parent, blas_leaf_parent, tlas_node_parent, tlas_leaf_parent;
     std::vector<float> perlin_vec;
     TextureRec env_image;
 };
@@ -111,7 +119,8 @@ int host_build(SceneImpl &s);  // BLAS per mesh, instance boxes, TLAS; fills tla
 bool host_tri_may_reject(const HostMesh &m, uint32_t t);
 
 // scene_device.cu
-int device_upload(SceneImpl &s);
-void device_free(SceneImpl &s);
+int device_upload(SceneImpl &s);                              // to the current device: replica 0
+int device_upload_replica(const SceneImpl &s, Replica &r, int device);  // a further copy on `device`
+void device_free(SceneImpl &s);                                // every replica
 
 }  // namespace pbrs

@@ -39,6 +39,8 @@ int device_upload(SceneImpl &s) {
     ds.tlas_nodes = s.tlas_nodes.data(); ds.blas_nodes = f.blas_nodes.data(); ds.tris = f.tris.data();
     ds.spheres = s.spheres.data(); ds.simples = s.simples.data(); ds.inst_trav = f.trav.data(); ds.inst_shade = f.shade.data(); ds.meshes = f.meshes.data();
     ds.tri_shade = f.tri_shade.data();
+    ds.blas_node_parent = f.blas_node_parent.data(); ds.blas_leaf_parent = f.blas_leaf_parent.data();
+    ds.tlas_node_parent = f.tlas_node_parent.data(); ds.tlas_leaf_parent = f.tlas_leaf_parent.data();
     ds.materials = s.materials.data(); ds.textures = f.textures.data(); ds.texels = f.texels.data();
     ds.perlin_vec = f.perlin_vec.data(); ds.perlin_perm = f.perlin_perm.data();
     ds.delta_lights = s.delta_lights.data(); ds.area_lights = s.area_lights.data();

@@ -10,8 +10,12 @@ scene is synthetic and procedurally generated (pbrs_b200/scenes.py), built once 
           timed with CUDA events, max over ranks).  N > 1: the frame's 64x64 tiles (or its sample
           indices for C5) are split over the ranks and the partial films summed with an NCCL
           reduce inside the timed region -- total work fixed ("strong").
-  e2e     the same metric through pbrs_render with a HOST film buffer: the per-step host->device
-          traffic (tile list) and the device->host film copy are inside the timed region.
+  e2e     the same metric through the public API with a HOST film: pbrs_render into a page-locked
+          film (N = 1), pbrs_b200.dist.render_sharded into one shared host film (N > 1: every
+          rank copies its own tiles straight into it; C5: NCCL reduce, then one copy out).  The
+          per-step host->device traffic and the device->host film copy are inside the timed region.
+  film_crc32  CRC-32 of rank 0's film after the last timed step (device leg) and of the host film
+          (e2e leg): for a tile split both are the same value at N = 1, 2, 4, 8.
   roofline  the closest-hit traversal kernel (k_extend): algorithmic bytes (SURVEY.md 8d formula,
           counters from one untimed PBRS_FLAG_COUNT_TRAVERSAL frame) / its summed launch time
           (CUDA events between launches, PBRS_FLAG_TIME_STAGES frames) vs the measured HBM copy peak.
@@ -28,6 +32,7 @@ import sys
 import tempfile
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -205,7 +210,7 @@ def main():
     import torch.distributed as dist
 
     from pbrs_b200 import _ffi
-    from pbrs_b200.dist import film_reduce, split_for
+    from pbrs_b200.dist import SharedHostFilm, film_reduce, render_sharded, split_for
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,6 +260,7 @@ def main():
         step_device()
     e1.record(stream)
     barrier()
+    film_crc = zlib.crc32(film.cpu().numpy().tobytes()) if rank == 0 else 0  # the whole frame, as the last timed step left it
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -271,28 +277,20 @@ def main():
             for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total"):
                 st_time[k] = min(st_time[k], s[k])
 
-    # e2e leg: host film buffer, copies inside the timed region
-    host = np.zeros((H, W, 3), np.float32)
-    import ctypes as C
-    from pbrs_b200 import _capi as K
-    o = h.make_opts(**kw)
-    hp = host.ctypes.data_as(K.c_float_p)
+    # e2e leg: one host film shared by the ranks (page-locked), copies inside the timed region
+    host = SharedHostFilm(H, W, api)
+    e2e_kw = dict(integrator=integrator, msaa=msaa, max_depth=5, split=split, paths_in_flight=args.paths_in_flight, host_film=host,
+                  device_film=film if (world > 1 and split == "samples") else None)
     for _ in range(1 if ms_step > 2000.0 else args.warmup):
-        api["render"](h.ptr, C.byref(o), hp, None)
+        render_sharded(h, **e2e_kw)
+    host.array[...] = 0.0
     barrier()
     t0 = time.perf_counter()
     step_times = []
     for _ in range(args.steps):
         t_step = time.perf_counter()
-        rc = api["render"](h.ptr, C.byref(o), hp, None)
-        assert rc == 0, h.last_error()
+        render_sharded(h, **e2e_kw)
         step_times.append((time.perf_counter() - t_step) * 1e3)
-        if world > 1:
-            # host-side combine of the ranks' films: stage through the device film and NCCL
-            film.copy_(torch.from_numpy(host), non_blocking=False)
-            film_reduce(film, None)
-            if rank == 0:
-                host[...] = film.cpu().numpy()
     barrier()
     e2e_s = time.perf_counter() - t0
     if os.environ.get("PBRS_BENCH_DEBUG"):
@@ -301,6 +299,9 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_step = float(te.item()) / args.steps
+    e2e_crc = zlib.crc32(host.array.tobytes()) if rank == 0 else 0
+    host_pinned = host.registered
+    host.close()
 
     # the sampler ran from the warm-up through the timed, roofline and e2e legs (all under load)
     clk = clocks.stop() if rank == 0 else None
@@ -312,6 +313,9 @@ def main():
     n_samples, n_ext, n_sh = [float(x) for x in cnt.tolist()]
 
     if rank == 0:
+        import ctypes as C
+        from pbrs_b200 import _capi as K
+        sizeof_opts = C.sizeof(K.RenderOpts)  # what crosses host -> device per step: the launch parameters (the tile list is cached on the device)
         peak, peak_src = hbm_peak()
         ext_b = extend_bytes(st_count)
         n_launch = max(1, st_time["launches_extend"])
@@ -328,8 +332,12 @@ def main():
             "mrays_per_s": (n_ext + n_sh) / (ms_step * 1e-3) / 1e6,
             "frame_ms": ms_step,
             "clocks": clk,
+            "film_crc32": f"{film_crc:08x}",
             "e2e": {"value": n_samples / e2e_step / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_step * 1e3,
-                    "h2d_bytes_per_step": int(4 * ((W + 63) // 64) * ((H + 63) // 64)), "d2h_bytes_per_step": int(W * H * 12)},
+                    "h2d_bytes_per_step": int(sizeof_opts), "d2h_bytes_per_step": int(W * H * 12), "film_crc32": f"{e2e_crc:08x}",
+                    "host_film": "one page-locked film shared by the ranks" if host_pinned else "pageable (registration failed)",
+                    "path": "pbrs_render" if world == 1 else ("render_sharded: own tiles -> shared host film" if split == "tiles"
+                                                              else "render_sharded: NCCL reduce -> one copy out")},
             "gpu_launches": int(st_time["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS/BLAS walk)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": measured_traffic(args.workload) if args.frame_scale == 1.0 else None,

@@ -19,7 +19,9 @@
  *     negative pbrs_status on failure; pbrs_last_error() has the message (thread-local).
  *   - nothing aborts: reference panics/asserts become either error codes (bad input) or the
  *     `would_panic` counters in pbrs_stats (numerical asserts on the hot path).
- *   - one pbrs_scene may be rendered from one host thread at a time.
+ *   - one pbrs_scene may be rendered from one host thread at a time, one frame in flight: the
+ *     path workspace, the counters and the cached CUDA graph belong to the scene (per device).
+ *     Every call restores the caller's current CUDA device before it returns.
  *   - there is NO CPU fallback: every render entry point fails with PBRS_ERR_NO_DEVICE when no
  *     CUDA device is usable.
  */
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PBRS_ABI_VERSION 1
+#define PBRS_ABI_VERSION 2
 
 typedef enum pbrs_status {
     PBRS_OK = 0,
@@ -184,6 +186,11 @@ typedef enum pbrs_split {
 #define PBRS_FLAG_NO_JITTER 4u       /* jitter (0,0) as the visualizers do, src/main.rs:170 */
 #define PBRS_FLAG_RAW_SUM 8u         /* leave the film as the un-normalised sample sum */
 #define PBRS_FLAG_NO_GRAPH 16u       /* enqueue a small frame kernel by kernel instead of replaying its CUDA graph */
+/* pbrs_render under a tile split: copy ONLY the tiles this rank owns into out_rgb (one 2-D copy per
+ * 64x64 tile) and leave every other pixel of the caller's buffer untouched.  Ranks that share one
+ * host film -- the device threads of a num_gpus > 1 call, or processes that map the same
+ * shared-memory buffer -- assemble the frame without any inter-GPU traffic. */
+#define PBRS_FLAG_OWN_TILES_ONLY 32u
 
 typedef struct pbrs_render_opts {
     int32_t integrator;  /* pbrs_integrator */
@@ -195,7 +202,14 @@ typedef struct pbrs_render_opts {
     int32_t split;       /* pbrs_split */
     uint32_t crop_x, crop_y, crop_w, crop_h; /* crop_w == 0: full frame */
     uint32_t flags;      /* PBRS_FLAG_* */
-    uint32_t paths_in_flight; /* 0 = library default */
+    uint32_t paths_in_flight; /* 0 = library default (16 Mi paths); values below 64 Ki are raised to 64 Ki */
+    /* 0 or 1: the device that was current at pbrs_scene_commit.  N > 1 (pbrs_render only, with
+     * rank = 0 and world_size <= 1): this ONE call spreads the frame over N CUDA devices -- the
+     * commit device and the N-1 lowest-numbered others; the scene is replicated on first use --
+     * splitting it by `split`, and returns the whole film: src/main.rs:189-235 gets N GPUs from
+     * one call.  Tiles: every device copies its own tiles straight into out_rgb.  Samples: the
+     * partial sums are added by one kernel on the first device over NVLink peer memory. */
+    int32_t num_gpus;
 } pbrs_render_opts;
 
 #define PBRS_NUM_PANIC_KINDS 16
@@ -247,6 +261,23 @@ int pbrs_render(const pbrs_scene *, const pbrs_render_opts *, float *out_rgb,
  * stream) and the call returns without synchronising unless stats are requested. */
 int pbrs_render_device(const pbrs_scene *, const pbrs_render_opts *, float *d_film,
                        void *cuda_stream, pbrs_stats *stats_or_null);
+
+/* After the caller has synchronised the stream a pbrs_render_device frame was enqueued on: fails
+ * (PBRS_ERR_UNSUPPORTED) if a traversal stack overflowed during that frame.  pbrs_render,
+ * pbrs_render_ids and pbrs_render_samples check this themselves.  (pbrs_scene_commit rejects every
+ * scene whose BVH depths could overflow the stack, so this is defence in depth.) */
+int pbrs_check_last_frame(const pbrs_scene *);
+
+/* Page-locked host memory for the film: the DMA target of pbrs_render's device-to-host copies
+ * (a pageable out_rgb works too, through the driver's staging copies: about half the speed).
+ * pbrs_film_alloc returns width*height*3 floats usable from every device (NULL on failure);
+ * pbrs_host_register pins a buffer the caller already owns -- e.g. the Vec<Color> of
+ * src/main.rs:219 -- until pbrs_host_unregister (call it before freeing the memory). */
+float *pbrs_film_alloc(uint32_t width, uint32_t height);
+void pbrs_film_free(float *);
+int pbrs_host_register(void *ptr, uint64_t bytes);
+int pbrs_host_unregister(void *ptr);
+int pbrs_device_count(void); /* usable CUDA devices (0 if none) */
 
 /* Parity side channels (host buffers; any pointer may be NULL).
  * Primary hit of sample `sample_index` of each pixel of the crop: instance id, primitive id

@@ -491,12 +491,16 @@ private:
 
 // The image_map computation of src/main.rs:189-235: every pixel, msaa*msaa stratified samples,
 // integrator depth 5, box average.  Row-major, row 0 = top -- what write_exr consumes.
-inline std::vector<Color> render(Scene &scene, Integrator integrator, uint32_t msaa, pbrs_stats *stats = nullptr, uint64_t seed = 0x5EED) {
+// num_gpus > 1: the one call spreads the frame over that many devices (tiles, or samples with
+// split = PBRS_SPLIT_SAMPLES) and still returns the whole film.
+inline std::vector<Color> render(Scene &scene, Integrator integrator, uint32_t msaa, pbrs_stats *stats = nullptr, uint64_t seed = 0x5EED,
+                                 int num_gpus = 1, int split = PBRS_SPLIT_TILES) {
     pbrs_scene *s = scene.commit();
     auto wh = scene.camera().resolution();
     std::vector<Color> film(size_t(wh.first) * wh.second);
     pbrs_render_opts o{};
     o.integrator = int(integrator); o.msaa = msaa; o.max_depth = 5; o.seed = seed; o.rank = 0; o.world_size = 1;
+    o.num_gpus = num_gpus; o.split = split;
     check(pbrs_render(s, &o, &film[0].r, stats), "render");
     return film;
 }

@@ -149,9 +149,10 @@ inline PlyMesh load_ply(const std::string &path) {
     };
     auto type_size = [](const std::string &n) { return (n == "uchar" || n == "uint8") ? 1 : n == "short" ? 2 : (n == "int" || n == "uint") ? 4 : 0; };  // :14-21
     auto count = [](const std::string &n, long &out) {
-        if (n.empty() || n.find_first_not_of("0123456789") != std::string::npos) return false;
+        // at most 10 digits and below 2^31: longer counts would overflow the size arithmetic below (and std::stol throws)
+        if (n.empty() || n.size() > 10 || n.find_first_not_of("0123456789") != std::string::npos) return false;
         out = std::stol(n);
-        return true;
+        return out < (1L << 31);
     };
     if (line() != "ply") throw Error(PBRS_ERR_INVALID_ARG, "ply: Header isn't ply");
     std::vector<std::string> fw = split(line());
@@ -182,7 +183,7 @@ inline PlyMesh load_ply(const std::string &path) {
         return v;
     };
     const size_t stride = props.size();
-    if (pos + size_t(nv) * stride * 4 > data.size()) throw Error(PBRS_ERR_INVALID_ARG, "ply: vertex block is truncated");
+    if (pos > data.size() || (stride != 0 && size_t(nv) > (data.size() - pos) / (stride * 4))) throw Error(PBRS_ERR_INVALID_ARG, "ply: vertex block is truncated");
     std::vector<float> vb(size_t(nv) * stride);
     for (size_t k = 0; k < vb.size(); ++k) { uint32_t u = u_at(pos + 4 * k, 4); std::memcpy(&vb[k], &u, 4); }
     pos += vb.size() * 4;

@@ -18,7 +18,7 @@ MTL_DIFFUSE_LIGHT, MTL_PLASTIC, MTL_UBER, MTL_SUBSTRATE = 5, 6, 7, 8
 ENV_BLUE_SKY, ENV_DARK_ROOM, ENV_DUSK = 0, 1, 2
 INTEGRATOR_DIRECT, INTEGRATOR_PATH = 0, 1
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
-FLAG_COUNT_TRAVERSAL, FLAG_TIME_STAGES, FLAG_NO_JITTER, FLAG_RAW_SUM, FLAG_NO_GRAPH = 1, 2, 4, 8, 16
+FLAG_COUNT_TRAVERSAL, FLAG_TIME_STAGES, FLAG_NO_JITTER, FLAG_RAW_SUM, FLAG_NO_GRAPH, FLAG_OWN_TILES_ONLY = 1, 2, 4, 8, 16, 32
 
 ERR_INVALID_ARG, ERR_STATE, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_OOM = -1, -2, -3, -4, -5, -6
 
@@ -51,6 +51,7 @@ class RenderOpts(C.Structure):
         ("crop_x", C.c_uint32), ("crop_y", C.c_uint32), ("crop_w", C.c_uint32), ("crop_h", C.c_uint32),
         ("flags", C.c_uint32),
         ("paths_in_flight", C.c_uint32),
+        ("num_gpus", C.c_int32),
     ]
 
 
@@ -137,6 +138,12 @@ SCENE_API = {
 PRODUCT_ONLY_API = {
     "render_device": (C.c_int, [P, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
     "abi_version": (C.c_int, []),
+    "check_last_frame": (C.c_int, [P]),
+    "film_alloc": (C.c_void_p, [C.c_uint32, C.c_uint32]),
+    "film_free": (None, [C.c_void_p]),
+    "host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "host_unregister": (C.c_int, [C.c_void_p]),
+    "device_count": (C.c_int, []),
 }
 
 # every symbol include/pbrs_gpu.h declares (checked by tests/test_abi.py)

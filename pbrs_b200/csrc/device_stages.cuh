@@ -33,6 +33,11 @@ struct PathBuffers {
     f4 *sh_c;   // c1.g, c1.b, c2.g, c2.b
     f4 *sh_b;   // multiplier rgb (path: beta before the bounce; specular stage: f), 1/light_pdf
     float *sh_m;  // < 0: path mode (rad += beta * X); >= 0: specular stage (rad += (X * f) * m)
+    // surface record of the split shade kernels (hit reconstruction -> scatter), 64 bytes per path:
+    f4 *sf_p;   // pos.xyz, u
+    f4 *sf_n;   // normal.xyz, v
+    f4 *sf_w;   // wo.xyz, material id (bits)
+    f4 *sf_t;   // tangent.xyz, t
     uint32_t *queue[2];            // extend queues (ping-pong between bounces)
     uint32_t *cls_queue[PBRS_NUM_CLS];  // shade queues, one per material class, filled by the extend kernel
     uint32_t *shadow_queue;
@@ -379,6 +384,83 @@ struct ShadeOut {
 // ---------------------------------------------------------------------------------------------
 // shade, path integrator: the body of the bounce loop, src/pathintegrator.rs:14-73
 // ---------------------------------------------------------------------------------------------
+// The two halves of the split shade kernels (kernels.cu PBRS_SHADE_SPLIT): `surface` = part 1 for
+// every hit of a heavy material class, leaving the world-space Interaction in the path's 64-byte
+// surface record; `scatter` = parts 2 and 3 from that record.  Same operations, same order as the
+// one-piece body; the Interaction just crosses HBM as its own bit patterns.
+PB_DEV void stage_shade_surface(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, int bounce, Diag &dg) {
+    Ray ray = load_ray(pb, j);
+    u4 hr;
+#ifdef __CUDA_ARCH__
+    { uint4 v = *reinterpret_cast<const uint4 *>(pb.hit + j); hr.x = v.x; hr.y = v.y; hr.z = v.z; hr.w = v.w; }
+#else
+    hr = pb.hit[j];
+#endif
+    Isect h;
+    uint32_t mtl_id = 0;
+    reconstruct_hit(sc, ray, hr.y, hr.z, h, mtl_id, dg);
+    f4 bt = load_f4(pb.beta + j);
+    if (bounce == 0 || (f2u(bt.w) & 1u) != 0u) {  // :19-22
+        f4 rd = load_f4(pb.rad + j);
+        color beta = mkc(bt.x, bt.y, bt.z), radiance = mkc(rd.x, rd.y, rd.z);
+        color env = eval_env(sc, ray.d, dg);
+        (void)env;
+        radiance = radiance + beta * mtl_emission(sc.materials[mtl_id]);
+        store_f4(pb.rad + j, radiance.r, radiance.g, radiance.b, 0.0f);
+    }
+    store_f4(pb.sf_p + j, h.pos.x, h.pos.y, h.pos.z, h.u);
+    store_f4(pb.sf_n + j, h.normal.x, h.normal.y, h.normal.z, h.v);
+    store_f4(pb.sf_w + j, h.wo.x, h.wo.y, h.wo.z, u2f(mtl_id));
+    store_f4(pb.sf_t + j, h.tangent.x, h.tangent.y, h.tangent.z, h.t);
+}
+template <int CLS>
+PB_DEV ShadeOut stage_shade_scatter(const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j,
+                                    int bounce, Diag &dg) {
+    constexpr int K = cls_lobe_kind(CLS);
+    ShadeOut out;
+    out.next = false; out.shadow_rays = 0;
+    const f4 sp = load_f4(pb.sf_p + j), sn = load_f4(pb.sf_n + j), sw = load_f4(pb.sf_w + j), st = load_f4(pb.sf_t + j);
+    Isect h;
+    h.pos = mk(sp.x, sp.y, sp.z); h.u = sp.w;
+    h.normal = mk(sn.x, sn.y, sn.z); h.v = sn.w;
+    h.wo = mk(sw.x, sw.y, sw.z);
+    h.tangent = mk(st.x, st.y, st.z); h.t = st.w;
+    const uint32_t mtl_id = f2u(sw.w);
+    const f4 bt = load_f4(pb.beta + j), rdir = load_f4(pb.ray_d + j);
+    color beta = mkc(bt.x, bt.y, bt.z);
+    const vec3 ray_d = mk(rdir.x, rdir.y, rdir.z);
+    Sampler smp = make_sampler(fp, decode_path(fp, bp, j));
+    const uint32_t base = 2u + 8u * (uint32_t)bounce;
+    const MaterialRec &m = sc.materials[mtl_id];
+    Lobes L;
+    bxdfs_at<CLS>(sc, m, h, L, dg);  // :31
+    Frame fr = bsdf_frame(h, dg);
+    ShadowOut so;
+    out.shadow_rays = sample_one_light<K>(sc, h, L, fr, smp, base, so, dg);  // :35
+    if (out.shadow_rays > 0) store_shadow(pb, j, so, beta, -1.0f);
+    float r0 = smp.f(base + 5), r1 = smp.f(base + 6);  // :46
+    color f;
+    vec3 wi;
+    Prob pr;
+    bsdf_sample<K>(fr, L, -ray_d, r0, r1, f, wi, pr, dg);  // :47
+    if (is_black(f) || pr.v == 0.0f) return out;  // :48
+    bool specular_bounce = pr.is_mass;             // :55
+    beta = beta * f * dot(wi, h.normal) * (1.0f / pr.v);  // :61 (Q7: signed cosine)
+    Ray nr = spawn_ray(h, wi);                     // :62
+    if (bounce > 3) {                              // :65-71
+        float q = fmaxf(1.0f - luminance(beta), 0.05f);
+        if (smp.f(base + 7) < q) return out;
+        beta = beta * (1.0f / (1.0f - q));
+    }
+    if (bounce + 1 >= fp.max_depth) return out;
+    store_f4(pb.ray_o + j, nr.o.x, nr.o.y, nr.o.z, nr.t_max);
+    store_f4(pb.ray_d + j, nr.d.x, nr.d.y, nr.d.z, 0.0f);
+    store_f4(pb.beta + j, beta.r, beta.g, beta.b, u2f(specular_bounce ? 1u : 0u));
+    out.next = true;
+    return out;
+}
+
+// The same body in one piece (the unsplit shade kernels and the host build).
 template <int CLS>
 PB_DEV ShadeOut stage_shade_path(const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j,
                                  int bounce, Diag &dg) {

@@ -50,6 +50,9 @@ PB_DEV bool ref_at_leaf(uint32_t n) { return (int32_t)n < -2; }
 #ifndef PBRS_BOX_FMA
 #define PBRS_BOX_FMA 0
 #endif
+#ifndef PBRS_PREFETCH_CHILDREN
+#define PBRS_PREFETCH_CHILDREN 0
+#endif
 
 struct BoxTest {
     bool pass;     // t_low <= min(min_el, t_max): exactly the reference's outcome
@@ -225,23 +228,34 @@ struct Walk {
         const bool f = is_fin(rd.x) && is_fin(rd.y) && is_fin(rd.z) && !any_nan(o);
         bits = (d.x > 0.0f ? 1u : 0u) | (d.y > 0.0f ? 2u : 0u) | (d.z > 0.0f ? 4u : 0u) | (f ? 8u : 0u) | mesh_bit;
 #if PBRS_BOX_FMA
-        nord = mk(-(o.x * rd.x), -(o.y * rd.y), -(o.z * rd.z));
-        c0 = fmaf(fmaxf(fmaxf(fabsf(nord.x), fabsf(nord.y)), fabsf(nord.z)), 2.384185791015625e-7f, PBRS_BOX_TINY);
+        set_fma_terms();
 #endif
     }
-    // World-ray state parked for the duration of a mesh walk (restored bit for bit; rd, bits and the
-    // FMA terms are recomputed from o and d by the same operations).
+#if PBRS_BOX_FMA
+    PB_DEV void set_fma_terms() {
+        nord = mk(-(o.x * rd.x), -(o.y * rd.y), -(o.z * rd.z));
+        c0 = fmaf(fmaxf(fmaxf(fabsf(nord.x), fabsf(nord.y)), fabsf(nord.z)), 2.384185791015625e-7f, PBRS_BOX_TINY);
+    }
+#endif
+    // World-ray state parked for the duration of a mesh walk (restored bit for bit; three IEEE
+    // divisions for rd at 3 of 32 lanes cost more than three loads, ncu r2).
     PB_DEV void save_world() {
         st.park_set(0, f2u(o.x)); st.park_set(1, f2u(o.y)); st.park_set(2, f2u(o.z));
         st.park_set(3, f2u(d.x)); st.park_set(4, f2u(d.y)); st.park_set(5, f2u(d.z));
         st.park_set(6, f2u(t_max));
-        if (!ANY) { st.park_set(7, f2u(best.t)); st.park_set(8, best.inst); st.park_set(9, best.tri); st.park_set(10, cur_inst); }
+        st.park_set(7, f2u(rd.x)); st.park_set(8, f2u(rd.y)); st.park_set(9, f2u(rd.z)); st.park_set(10, bits);
+        if (!ANY) { st.park_set(11, f2u(best.t)); st.park_set(12, best.inst); st.park_set(13, best.tri); st.park_set(14, cur_inst); }
     }
     PB_DEV void restore_world() {
-        const vec3 wo = mk(u2f(st.park_get(0)), u2f(st.park_get(1)), u2f(st.park_get(2)));
-        const vec3 wd = mk(u2f(st.park_get(3)), u2f(st.park_get(4)), u2f(st.park_get(5)));
-        set_space(wo, wd, u2f(st.park_get(6)), 0u);
-        if (!ANY) { best.t = u2f(st.park_get(7)); best.inst = st.park_get(8); best.tri = st.park_get(9); cur_inst = st.park_get(10); }
+        o = mk(u2f(st.park_get(0)), u2f(st.park_get(1)), u2f(st.park_get(2)));
+        d = mk(u2f(st.park_get(3)), u2f(st.park_get(4)), u2f(st.park_get(5)));
+        t_max = u2f(st.park_get(6));
+        rd = mk(u2f(st.park_get(7)), u2f(st.park_get(8)), u2f(st.park_get(9)));
+        bits = st.park_get(10);
+#if PBRS_BOX_FMA
+        set_fma_terms();
+#endif
+        if (!ANY) { best.t = u2f(st.park_get(11)); best.inst = st.park_get(12); best.tri = st.park_get(13); cur_inst = st.park_get(14); }
     }
     // exact pass of the stacked child `ref` (the rare re-test): its box is in its parent's record
     PB_DEV bool exact_child(const DeviceScene &sc, uint32_t ref, float extent) const {
@@ -288,6 +302,10 @@ struct Walk {
         const PairTest pt = test_pair(q0, q1, q2, o, d, rd, o, PBRS_BOX_TINY, fast(), t_max, !ANY && !in_mesh());
 #endif
         const uint32_t lref = f2u(q3.x), rref = f2u(q3.y);  // leaf bit and run length are part of the link
+#if PBRS_PREFETCH_CHILDREN && defined(__CUDA_ARCH__)
+        // the right child's record while the boxes are being tested (the left one is the next record in preorder)
+        if ((int32_t)rref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + rref));
+#endif
         if (ANY) {
             // `left || right`, depth first (tlas/src/bvh.rs:105-113, blas.rs:478-495); the extent
             // never changes, so a pass is final.  (Visiting the nearer child first was measured:
@@ -305,8 +323,15 @@ struct Walk {
             // first and re-tested against the extent of the moment when it is popped
             const bool left_near = ((bits >> (f2u(q3.z) & 3u)) & 1u) != 0u;
             const bool np = left_near ? pt.lp : pt.rp, fp = left_near ? pt.rp : pt.lp;
-            if (fp) st.push(left_near ? rref : lref, left_near ? pt.rtl : pt.ltl, dg);
-            next = np ? (left_near ? lref : rref) : PBRS_NONE;
+            // (near fails, far passes: the far child would be pushed and popped right back against
+            // the unchanged extent -- the same outcome without the round trip through the stack)
+            const uint32_t nref = left_near ? lref : rref, fref = left_near ? rref : lref;
+            if (np) {
+                if (fp) st.push(fref, left_near ? pt.rtl : pt.ltl, dg);
+                next = nref;
+            } else {
+                next = fp ? fref : PBRS_NONE;
+            }
             return;
         }
         // tlas/src/bvh.rs:83-100: left, then right against whatever extent the left subtree leaves

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffe
 // phase 2 (one leaf or unwind) and, whenever enough lanes have run dry, hands them the next rays
 // of the warp's chunk of the queue (one atomicAdd on the launch's work cursor per chunk).
 #ifndef PBRS_REFILL_IDLE_LANES
-#define PBRS_REFILL_IDLE_LANES 20
+#define PBRS_REFILL_IDLE_LANES 8  // a refill costs no atomic (the warp owns a chunk of the queue): 8 beats 12 and 20 (profiles/r2_exp_coop_closest_refill_vote.log)
 #endif
 #ifndef PBRS_REFILL_IDLE_LANES_ANY
 #define PBRS_REFILL_IDLE_LANES_ANY PBRS_REFILL_IDLE_LANES
@@ -108,7 +108,7 @@ template <bool ANY> constexpr int kRefillIdleLanes = ANY ? PBRS_REFILL_IDLE_LANE
 #define PBRS_LEAF_VOTE_ANY 12  // any-hit leaves are cheap to wait for: C5 shadow -7 %, C3/C4 unchanged (profiles/r1_exp_anyhit_vote.log)
 #endif
 #ifndef PBRS_NODE_STEPS
-#define PBRS_NODE_STEPS 2  // node steps between two votes of the warp
+#define PBRS_NODE_STEPS 3  // node steps between two votes of the warp (3 beats 2 by 1-4 % of the extend time, 1 loses: profiles/r2_exp_*.log)
 #endif
 
 // `cnt` = this stage's counter block (PBRS_CNT_*).
@@ -118,6 +118,9 @@ template <bool ANY> constexpr int kRefillIdleLanes = ANY ? PBRS_REFILL_IDLE_LANE
 #ifndef PBRS_COOP_ANY
 #define PBRS_COOP_ANY 1
 #endif
+#ifndef PBRS_COOP_CLOSEST
+#define PBRS_COOP_CLOSEST 1  // with the stack in local memory: extend -4.5 % on C4 and C5; scenes of a few triangles lose 8 % and switch it off (DeviceScene::coop_closest)
+#endif
 
 // The walk's stack on the device: a ring of the TOP entries per lane in shared memory (entry s of
 // lane l at ring[s * kThreads + l]: one bank per lane, so a push or pop is one conflict-free
@@ -126,8 +129,14 @@ template <bool ANY> constexpr int kRefillIdleLanes = ANY ? PBRS_REFILL_IDLE_LANE
 // reading back from there only after the ring has run empty.  Entries [lo, sp) are in the ring,
 // [0, lo) in local memory.  The parked world-ray state of a mesh walk sits in local memory at
 // fixed slots (all lanes the same address offset: coalesced).
+// Measured (profiles/r2_exp_walker_v2_variants.log, r2_exp_coop_closest_refill_vote.log,
+// r2_exp_stack_prefetch_steps.log): the ring costs more than it saves -- extend +3.4 % on C4, +4.7 % on
+// C5, +6 % on C3 against the same walk with its stack in local memory, and a ring of 4 entries is worse
+// than one of 8.  Local-memory stack traffic is 2.6 % of the instructions and hits L1 88 % of the time
+// (ncu, profiles/r2_stack_counters.md); the ring adds its full / empty bookkeeping to every push and
+// pop.  It therefore stays a build option (-DPBRS_SMEM_STACK=1) and the default stack is local memory.
 #ifndef PBRS_SMEM_STACK
-#define PBRS_SMEM_STACK 1
+#define PBRS_SMEM_STACK 0
 #endif
 #ifndef PBRS_SMEM_STACK_CLOSEST
 #define PBRS_SMEM_STACK_CLOSEST 8   // (link, t_low) pairs: 8 KB per block of 128 threads
@@ -263,7 +272,9 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
             const unsigned m_adv = __ballot_sync(0xFFFFFFFFu, w.advancing());
             const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, w.at_leaf());
             if (m_adv == 0u || __popc(m_leaf) >= vote) break;
-#pragma unroll
+            // (a real loop: three unrolled copies of the step push the kernel past 50 KB of SASS and the
+            // extend time up 10 %, profiles/r2_exp_shade_phased_and_code_size.log)
+#pragma unroll 1
             for (int k = 0; k < PBRS_NODE_STEPS; ++k)
                 if (w.advancing()) w.advance(sc, dg, tc);
         }
@@ -321,6 +332,75 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
             }
         }
 #endif
+#if PBRS_COOP_CLOSEST
+        // ---- phase 2, closest-hit: the same spreading of (lane, triangle) pairs over the warp ----
+        // The leaf's triangles all see the extent of the pop and the winner is the smallest t, the
+        // FIRST of the run on ties (`t < best` in run order, shape/src/blas.rs:447-454): a segmented
+        // min over the run's lanes that only takes a later candidate when it is strictly smaller,
+        // then one compare against the walk's best.  Incoherent rays stand at their leaves 3-7
+        // lanes at a time (ncu, bounce 1 of C4): lane by lane the triangle code ran at 4-5 of 32 lanes.
+        if (!ANY && sc.coop_closest) {
+            __shared__ uint16_t coop_slots2[kThreads];
+            uint16_t *slot = coop_slots2 + (threadIdx.x & ~31u);
+            bool mine = w.at_leaf() && w.in_mesh() && ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) != 0u;
+            unsigned owners = __ballot_sync(0xFFFFFFFFu, mine);
+            while (owners) {
+                const uint32_t c = mine ? ((w.next >> PBRS_LEAF_COUNT_SHIFT) & 7u) : 0u;
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if ((int)lane_id() >= d) incl += v;
+                }
+                const uint32_t excl = incl - c;
+                const bool in_pass = mine && incl <= 32u;  // the first owner always fits (c <= 6)
+                if (in_pass)
+                    for (uint32_t k = 0; k < c; ++k) slot[excl + k] = (uint16_t)(lane_id() | (k << 5) | (c << 8));
+                const uint32_t total = __reduce_max_sync(0xFFFFFFFFu, in_pass ? incl : 0u);
+                __syncwarp();
+                const bool work = lane_id() < total;
+                const uint32_t e = work ? slot[lane_id()] : 0u;
+                const int src = (int)(e & 31u);
+                const uint32_t k = (e >> 5) & 7u, run = e >> 8;
+                Ray r;
+                r.o.x = __shfl_sync(0xFFFFFFFFu, w.o.x, src); r.o.y = __shfl_sync(0xFFFFFFFFu, w.o.y, src); r.o.z = __shfl_sync(0xFFFFFFFFu, w.o.z, src);
+                r.d.x = __shfl_sync(0xFFFFFFFFu, w.d.x, src); r.d.y = __shfl_sync(0xFFFFFFFFu, w.d.y, src); r.d.z = __shfl_sync(0xFFFFFFFFu, w.d.z, src);
+                r.t_max = __shfl_sync(0xFFFFFFFFu, w.t_max, src);
+                const uint32_t first = __shfl_sync(0xFFFFFFFFu, w.tri_base + (w.next & PBRS_LEAF_FIRST_MASK), src);
+                float val = PB_INF;
+                if (work) {
+                    const uint32_t s = first + k;
+                    const TriVerts tv = load_tri(sc.tris + s);
+                    float t;
+                    bool hit;
+                    if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { if (COUNT) tc.spheres++; hit = ball_test(tv.p0, tv.p1.x, r, false, t, dg); }
+                    else {
+                        if (COUNT) tc.tris++;
+                        if (EXT && (tv.flags & PBRS_TRI_CHECK_SHADING)) hit = mesh_tri_shade_t(sc, s, tv, r, t, dg);
+                        else hit = mesh_tri_hit_t(tv, r, t, dg);
+                    }
+                    if (hit) val = t;
+                }
+                uint32_t arg = k;
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {  // runs are <= 6 long
+                    const float ov = __shfl_down_sync(0xFFFFFFFFu, val, d);
+                    const uint32_t oa = __shfl_down_sync(0xFFFFFFFFu, arg, d);
+                    if (work && k + (uint32_t)d < run && ov < val) { val = ov; arg = oa; }  // strictly smaller only: the earlier triangle keeps a tie
+                }
+                const float bv = __shfl_sync(0xFFFFFFFFu, val, (int)(excl & 31u));
+                const uint32_t ba = __shfl_sync(0xFFFFFFFFu, arg, (int)(excl & 31u));
+                if (in_pass) {
+                    if (bv < w.l_best_t) { w.l_best_t = bv; w.l_best_tri = w.tri_base + (w.next & PBRS_LEAF_FIRST_MASK) + ba; }
+                    w.t_max = w.l_best_t;  // blas.rs:468
+                    w.next = PBRS_NONE;
+                    mine = false;
+                }
+                __syncwarp();
+                owners = __ballot_sync(0xFFFFFFFFu, mine);
+            }
+        }
+#endif
         // ---- phase 2: one leaf ----
         if (w.at_leaf()) w.leaf(sc, dg, tc);
         if (ANY) {
@@ -364,6 +444,22 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
 #ifndef PBRS_SHADE_BLOCKS_PER_SM
 #define PBRS_SHADE_BLOCKS_PER_SM 4
 #endif
+// PBRS_SHADE_SPLIT (path integrator): the classes with a large body -- Lambert, microfacet, multi-
+// lobe -- are shaded by two kernels instead of one: k_surface rebuilds the hit (one kernel for all
+// three classes: the code does not depend on the material) and leaves it in the path's 64-byte
+// surface record, k_scatter<class> does lobes, light sampling and BSDF sampling from the record.
+// Each half is well under the instruction-cache footprint and the register count of the one-piece
+// kernel (186 KB of SASS, 128 registers, 4.4 stall cycles per issue waiting for instructions:
+// profiles/r1_final3_ncu_shade_c4.md); the price is 128 bytes of state traffic per path and bounce.
+#ifndef PBRS_SHADE_SPLIT
+#define PBRS_SHADE_SPLIT 1
+#endif
+#ifndef PBRS_SURFACE_BLOCKS_PER_SM
+#define PBRS_SURFACE_BLOCKS_PER_SM 6
+#endif
+#ifndef PBRS_SCATTER_BLOCKS_PER_SM
+#define PBRS_SCATTER_BLOCKS_PER_SM 4
+#endif
 template <int CLS, int INTEGRATOR>
 __global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
                                                     uint32_t *next_queue, uint32_t *next_cnt, int bounce) {
@@ -378,6 +474,44 @@ __global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(De
             j = queue[i];
             so = INTEGRATOR == PBRS_INTEGRATOR_PATH ? stage_shade_path<CLS>(sc, pb, fp, bp, j, bounce, dg)
                                                     : stage_shade_direct<CLS>(sc, pb, fp, bp, j, bounce, dg);
+        }
+        uint32_t s1, s2;
+        warp_push2(next_count, so.next, shadow_count, so.shadow_rays > 0, s1, s2);
+        if (so.next) next_queue[s1] = j;
+        if (so.shadow_rays > 0) pb.shadow_queue[s2] = j;
+        rays += (uint32_t)so.shadow_rays;
+    }
+    __syncwarp();
+    warp_add_stat(pb.stats + kStatShadowRays, rays);
+    flush_diag(pb.stats, dg);
+}
+// the three heavy classes' queues, one after the other
+__global__ void __launch_bounds__(kThreads, PBRS_SURFACE_BLOCKS_PER_SM) k_surface(DeviceScene sc, PathBuffers pb, const uint32_t *cnt, int bounce) {
+    Diag dg; dg.panics = 0u;
+    const int classes[3] = {PBRS_CLS_LAMBERT, PBRS_CLS_MICROFACET, PBRS_CLS_MULTI};
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t *queue = pb.cls_queue[classes[c]];
+        PBRS_WARP_LOOP(cnt[PBRS_CNT_CLS + classes[c]], i, active) {
+            if (active) stage_shade_surface(sc, pb, queue[i], bounce, dg);
+        }
+    }
+    __syncwarp();
+    flush_diag(pb.stats, dg);
+}
+template <int CLS>
+__global__ void __launch_bounds__(kThreads, PBRS_SCATTER_BLOCKS_PER_SM) k_scatter(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
+                                                                                  uint32_t *next_queue, uint32_t *next_cnt, int bounce) {
+    Diag dg; dg.panics = 0u;
+    uint32_t rays = 0u;
+    const uint32_t *queue = pb.cls_queue[CLS];
+    uint32_t *next_count = next_cnt + PBRS_CNT_EXTEND, *shadow_count = cnt + PBRS_CNT_SHADOW;
+    PBRS_WARP_LOOP(cnt[PBRS_CNT_CLS + CLS], i, active) {
+        ShadeOut so; so.next = false; so.shadow_rays = 0;
+        uint32_t j = 0u;
+        if (active) {
+            j = queue[i];
+            so = stage_shade_scatter<CLS>(sc, pb, fp, bp, j, bounce, dg);
         }
         uint32_t s1, s2;
         warp_push2(next_count, so.next, shadow_count, so.shadow_rays > 0, s1, s2);
@@ -427,9 +561,11 @@ __global__ void __launch_bounds__(kThreads) k_write_samples(PathBuffers pb, Fram
     }
 }
 
+
 struct Grid {
     int extend, extend_ext, extend_count, shadow, shadow_ext, shadow_count, small;
     int shade[2][PBRS_NUM_CLS];
+    int surface, scatter[3];
 };
 
 template <int INTEGRATOR>
@@ -438,11 +574,21 @@ void launch_shade(const Grid &g, cudaStream_t stream, const DeviceScene &sc, con
     const int *gs = g.shade[INTEGRATOR];
     k_shade<PBRS_CLS_MISS, INTEGRATOR><<<gs[PBRS_CLS_MISS], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
     k_shade<PBRS_CLS_EMISSIVE, INTEGRATOR><<<gs[PBRS_CLS_EMISSIVE], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-    k_shade<PBRS_CLS_LAMBERT, INTEGRATOR><<<gs[PBRS_CLS_LAMBERT], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-    k_shade<PBRS_CLS_MICROFACET, INTEGRATOR><<<gs[PBRS_CLS_MICROFACET], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    if (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH) {
+        k_surface<<<g.surface, kThreads, 0, stream>>>(sc, pb, cnt, stage);
+        k_scatter<PBRS_CLS_LAMBERT><<<g.scatter[0], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        k_scatter<PBRS_CLS_MICROFACET><<<g.scatter[1], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        k_scatter<PBRS_CLS_MULTI><<<g.scatter[2], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    } else {
+        k_shade<PBRS_CLS_LAMBERT, INTEGRATOR><<<gs[PBRS_CLS_LAMBERT], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        k_shade<PBRS_CLS_MICROFACET, INTEGRATOR><<<gs[PBRS_CLS_MICROFACET], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        k_shade<PBRS_CLS_MULTI, INTEGRATOR><<<gs[PBRS_CLS_MULTI], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    }
     k_shade<PBRS_CLS_SPECULAR, INTEGRATOR><<<gs[PBRS_CLS_SPECULAR], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-    k_shade<PBRS_CLS_MULTI, INTEGRATOR><<<gs[PBRS_CLS_MULTI], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
 }
+// kernels launched by launch_shade
+template <int INTEGRATOR>
+constexpr int shade_launches() { return (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH) ? PBRS_NUM_CLS + 1 : PBRS_NUM_CLS; }
 template <int INTEGRATOR>
 void size_shade(Grid &g, int sms);
 
@@ -539,6 +685,10 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
         w.grid.shadow_ext = blocks_for(k_trace<true, false, true>, w.sms);
         w.grid.shadow_count = blocks_for(k_trace<true, true, true>, w.sms);
         w.grid.small = blocks_for(k_generate, w.sms);
+        w.grid.surface = blocks_for(k_surface, w.sms);
+        w.grid.scatter[0] = blocks_for(k_scatter<PBRS_CLS_LAMBERT>, w.sms);
+        w.grid.scatter[1] = blocks_for(k_scatter<PBRS_CLS_MICROFACET>, w.sms);
+        w.grid.scatter[2] = blocks_for(k_scatter<PBRS_CLS_MULTI>, w.sms);
         w.grid_ready = true;
     }
     if (!w.ev[0]) { CK(cudaEventCreate(&w.ev[0])); CK(cudaEventCreate(&w.ev[1])); }
@@ -551,8 +701,8 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
     if (w.capacity < capacity || w.n_lanes < n_lanes) {
         for (auto &p : w.slab) if (p) { cudaFree(p); p = nullptr; }
         w.capacity = 0; w.n_lanes = 0;
-        // 13 x 16-byte arrays + 1 float + (3 + PBRS_NUM_CLS) queues per path slot
-        size_t per = 13 * sizeof(f4) + sizeof(float) + (3 + PBRS_NUM_CLS) * sizeof(uint32_t);
+        // 16 x 16-byte arrays + 1 float + (3 + PBRS_NUM_CLS) queues per path slot
+        size_t per = 16 * sizeof(f4) + sizeof(float) + (3 + PBRS_NUM_CLS) * sizeof(uint32_t);
         size_t bytes = per * (size_t)capacity + 4096;
         for (int l = 0; l < n_lanes; ++l) {
             cudaError_t e = cudaMalloc(&w.slab[l], bytes);
@@ -564,7 +714,7 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
             pb.rad = (f4 *)take(16); pb.aux = (f4 *)take(16);
             pb.sh_o1 = (f4 *)take(16); pb.sh_d1 = (f4 *)take(16); pb.sh_o2 = (f4 *)take(16); pb.sh_d2 = (f4 *)take(16);
             pb.sh_c = (f4 *)take(16); pb.sh_b = (f4 *)take(16);
-            (void)take(16);  // spare
+            pb.sf_p = (f4 *)take(16); pb.sf_n = (f4 *)take(16); pb.sf_w = (f4 *)take(16); pb.sf_t = (f4 *)take(16);
             pb.sh_m = (float *)take(4);
             pb.queue[0] = (uint32_t *)take(4); pb.queue[1] = (uint32_t *)take(4); pb.shadow_queue = (uint32_t *)take(4);
             for (int c = 0; c < PBRS_NUM_CLS; ++c) pb.cls_queue[c] = (uint32_t *)take(4);
@@ -733,20 +883,22 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
             for (int stage = 0; stage < n_stages; ++stage) {
                 uint32_t *q_in = pb.queue[stage & 1], *q_out = pb.queue[(stage + 1) & 1];
                 uint32_t *cnt = pb.counts + PBRS_CNT_STRIDE * stage, *next_cnt = cnt + PBRS_CNT_STRIDE;
-                if (count_trav) k_trace<false, true, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
-                else if (sc.has_ext) k_trace<false, false, true><<<w.grid.extend_ext, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
-                else k_trace<false, false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_in, cnt);
+                const uint32_t *q_ext = q_in;
+                if (count_trav) k_trace<false, true, true><<<w.grid.extend_count, kThreads, 0, stream>>>(sc, pb, q_ext, cnt);
+                else if (sc.has_ext) k_trace<false, false, true><<<w.grid.extend_ext, kThreads, 0, stream>>>(sc, pb, q_ext, cnt);
+                else k_trace<false, false, false><<<w.grid.extend, kThreads, 0, stream>>>(sc, pb, q_ext, cnt);
                 ++launches; ++launches_extend;
                 mark(T_EXT);
                 if (tg.only_sample >= 0) break;
                 if (o.integrator == PBRS_INTEGRATOR_PATH) launch_shade<PBRS_INTEGRATOR_PATH>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
                 else launch_shade<PBRS_INTEGRATOR_DIRECT>(w.grid, stream, sc, pb, fp, bp, cnt, q_out, next_cnt, stage);
                 mark(T_SHADE);
-                if (count_trav) k_trace<true, true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
-                else if (sc.has_ext) k_trace<true, false, true><<<w.grid.shadow_ext, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
-                else k_trace<true, false, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, pb.shadow_queue, cnt);
+                const uint32_t *q_sh = pb.shadow_queue;
+                if (count_trav) k_trace<true, true, true><<<w.grid.shadow_count, kThreads, 0, stream>>>(sc, pb, q_sh, cnt);
+                else if (sc.has_ext) k_trace<true, false, true><<<w.grid.shadow_ext, kThreads, 0, stream>>>(sc, pb, q_sh, cnt);
+                else k_trace<true, false, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, q_sh, cnt);
                 mark(T_SHADOW);
-                launches += PBRS_NUM_CLS + 1; ++launches_shadow;
+                launches += (o.integrator == PBRS_INTEGRATOR_PATH ? shade_launches<PBRS_INTEGRATOR_PATH>() : shade_launches<PBRS_INTEGRATOR_DIRECT>()) + 1; ++launches_shadow;
             }
             if (tg.only_sample >= 0) {
                 k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
@@ -803,7 +955,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
                 for (int stage = 0; stage < n_stages; ++stage) {
                     ++launches; ++launches_extend;
                     if (tg.only_sample >= 0) break;
-                    launches += PBRS_NUM_CLS + 1; ++launches_shadow;
+                    launches += (o.integrator == PBRS_INTEGRATOR_PATH ? shade_launches<PBRS_INTEGRATOR_PATH>() : shade_launches<PBRS_INTEGRATOR_DIRECT>()) + 1; ++launches_shadow;
                 }
                 if (tg.only_sample >= 0) ++launches;
                 else launches += (tg.film ? 1 : 0) + (tg.samples ? 1 : 0);

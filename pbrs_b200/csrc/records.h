@@ -236,6 +236,7 @@ struct DeviceScene {
     uint32_t n_instances;
     uint32_t leaf_vote; // lanes waiting at a leaf that end the node phase of the closest-hit walk (kernels.cu)
     uint32_t has_mesh; // any BLAS at all (a scene of spheres skips the cooperative leaf phase)
+    uint32_t coop_closest; // closest-hit walks test their leaf runs cooperatively (scenes with >= 1024 triangles)
     uint32_t has_ext;  // any quad / cuboid / disk instance or sphere BLAS: selects the EXT traversal kernels
 };
 

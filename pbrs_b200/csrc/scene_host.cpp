@@ -685,6 +685,8 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     ds.leaf_vote = (!s.meshes.empty() && s.instances.size() >= PBRS_MANY_INSTANCES) ? 12u : 8u;
     if (const char *e = std::getenv("PBRS_LEAF_VOTE_CLOSEST")) ds.leaf_vote = (uint32_t)std::atoi(e);  // development knob
     ds.has_mesh = s.meshes.empty() ? 0u : 1u;
+    ds.coop_closest = f.tris.size() >= 1024 ? 1u : 0u;  // a Cornell box (34 triangles) loses 8 % of its extend time to the bookkeeping
+    if (const char *e = std::getenv("PBRS_COOP_CLOSEST")) ds.coop_closest = (uint32_t)std::atoi(e);  // development knob
     ds.has_ext = s.simples.empty() ? 0u : 1u;
     for (const HostMesh &m : s.meshes)
         if (!m.balls.empty()) ds.has_ext = 1u;

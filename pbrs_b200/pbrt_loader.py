@@ -233,9 +233,9 @@ def load_ply(path):
         if len(w) < 3:
             raise PbrtError(f"ply: Can't handle the line {ln}")
         if w[:2] == ["element", "vertex"] and len(w) == 3:
-            nv = int(w[2]) if w[2].isdigit() else None
+            nv = int(w[2]) if (w[2].isdigit() and len(w[2]) <= 10 and int(w[2]) < 2 ** 31) else None  # same limit as the C++ loader
         elif w[:2] == ["element", "face"] and len(w) == 3:
-            nf = int(w[2]) if w[2].isdigit() else None
+            nf = int(w[2]) if (w[2].isdigit() and len(w[2]) <= 10 and int(w[2]) < 2 ** 31) else None
         elif w[:2] == ["property", "float"] and len(w) == 3:
             props.append(w[2])
         elif w[:2] == ["property", "list"] and len(w) == 5 and w[4] == "vertex_indices":

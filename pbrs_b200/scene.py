@@ -303,7 +303,7 @@ class SceneHandle:
 
     @staticmethod
     def make_opts(integrator="path", msaa=1, max_depth=5, seed=0x5EED, rank=0, world_size=1, split="tiles",
-                  crop=None, flags=0, paths_in_flight=0):
+                  crop=None, flags=0, paths_in_flight=0, num_gpus=0):
         o = K.RenderOpts()
         o.integrator = K.INTEGRATOR_PATH if integrator == "path" else K.INTEGRATOR_DIRECT
         o.msaa, o.max_depth, o.seed = int(msaa), int(max_depth), int(seed)
@@ -313,15 +313,19 @@ class SceneHandle:
             o.crop_x, o.crop_y, o.crop_w, o.crop_h = [int(c) for c in crop]
         o.flags = int(flags)
         o.paths_in_flight = int(paths_in_flight)
+        o.num_gpus = int(num_gpus)
         return o
 
     def _crop_wh(self, o):
         return (o.crop_w, o.crop_h) if o.crop_w else (self.width, self.height)
 
-    def render(self, want_stats=True, **kw):
-        """Film [H, W, 3] float32 (row 0 = top), stats dict.  src/main.rs:189-235."""
+    def render(self, want_stats=True, out=None, **kw):
+        """Film [H, W, 3] float32 (row 0 = top), stats dict.  src/main.rs:189-235.
+        out: an existing [H, W, 3] float32 film to render into (e.g. a page-locked one)."""
         o = self.make_opts(**kw)
-        out = np.zeros((self.height, self.width, 3), np.float32)
+        if out is None:
+            out = np.zeros((self.height, self.width, 3), np.float32)
+        assert out.shape == (self.height, self.width, 3) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
         st = K.Stats()
         self._check(self.api["render"](self.ptr, C.byref(o), out.ctypes.data_as(K.c_float_p),
                                        C.byref(st) if want_stats else None), "render")

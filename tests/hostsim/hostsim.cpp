@@ -52,7 +52,7 @@ int device_upload(SceneImpl &s) {
 namespace {
 
 struct Sim {
-    std::vector<f4> a[12];
+    std::vector<f4> a[16];
     std::vector<u4> hit;
     std::vector<float> sh_m;
     std::vector<uint32_t> q0, q1, sq, cq[PBRS_NUM_CLS];
@@ -65,6 +65,7 @@ struct Sim {
         pb.ray_o = a[0].data(); pb.ray_d = a[1].data(); pb.hit = hit.data(); pb.beta = a[2].data(); pb.rad = a[3].data();
         pb.aux = a[4].data(); pb.sh_o1 = a[5].data(); pb.sh_d1 = a[6].data(); pb.sh_o2 = a[7].data(); pb.sh_d2 = a[8].data();
         pb.sh_c = a[9].data(); pb.sh_b = a[10].data(); pb.sh_m = sh_m.data();
+        pb.sf_p = a[12].data(); pb.sf_n = a[13].data(); pb.sf_w = a[14].data(); pb.sf_t = a[15].data();
         pb.queue[0] = q0.data(); pb.queue[1] = q1.data(); pb.shadow_queue = sq.data();
         pb.capacity = n;
     }
@@ -92,6 +93,14 @@ ShadeOut shade_cls(int integrator, const DeviceScene &sc, const PathBuffers &pb,
 }
 ShadeOut shade_dispatch(int cls, int integrator, const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp, uint32_t j,
                         int stage, Diag &dg) {
+    // like the kernels (PBRS_SHADE_SPLIT): the heavy classes of the path integrator go through the
+    // surface record -- hit reconstruction first, then lobes / light sampling / BSDF sampling from it
+    if (integrator == PBRS_INTEGRATOR_PATH && (cls == PBRS_CLS_LAMBERT || cls == PBRS_CLS_MICROFACET || cls == PBRS_CLS_MULTI)) {
+        stage_shade_surface(sc, pb, j, stage, dg);
+        if (cls == PBRS_CLS_LAMBERT) return stage_shade_scatter<PBRS_CLS_LAMBERT>(sc, pb, fp, bp, j, stage, dg);
+        if (cls == PBRS_CLS_MICROFACET) return stage_shade_scatter<PBRS_CLS_MICROFACET>(sc, pb, fp, bp, j, stage, dg);
+        return stage_shade_scatter<PBRS_CLS_MULTI>(sc, pb, fp, bp, j, stage, dg);
+    }
     switch (cls) {
     case PBRS_CLS_MISS: return shade_cls<PBRS_CLS_MISS>(integrator, sc, pb, fp, bp, j, stage, dg);
     case PBRS_CLS_EMISSIVE: return shade_cls<PBRS_CLS_EMISSIVE>(integrator, sc, pb, fp, bp, j, stage, dg);

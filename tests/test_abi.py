@@ -31,7 +31,7 @@ def test_library_exports_every_header_symbol():
 
 def test_abi_version_and_struct_sizes():
     api = _ffi.load()
-    assert api["abi_version"]() == 1
+    assert api["abi_version"]() == 2
     # sizes implied by the header's field lists on x86-64
     assert C.sizeof(K.MaterialDesc) == 4 * 5 + 12 + 12 + 16 + 4
     assert C.sizeof(K.RenderOpts) == 64
@@ -114,11 +114,30 @@ def test_product_never_touches_the_oracle():
                 assert "hostsim" not in text or f.endswith(".cuh"), os.path.join(dirpath, f)
 
 
-def test_integration_doc_binds_every_entry_point():
-    """INTEGRATION.md shows the Rust `extern "C"` item of every function include/pbrs_gpu.h declares."""
-    import re
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "pbrs_gpu.h")).read(), flags=re.S)
+def test_rust_bindings_are_generated_from_the_header_and_complete():
+    """ffi/pbrs_gpu.rs (the Rust `extern "C"` side of the boundary) is generated from
+    include/pbrs_gpu.h by tools/gen_rust_ffi.py: it must be up to date, bind every function the header
+    declares with the argument count of the ctypes mirror, and carry the structs field for field."""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"]).returncode == 0, \
+        "ffi/pbrs_gpu.rs is stale: run python tools/gen_rust_ffi.py"
+    rs = open(os.path.join(ROOT, "ffi", "pbrs_gpu.rs")).read()
+    header = re.sub(r"/\*.*?\*/", "", _header(), flags=re.S)
     declared = set(re.findall(r"\b(pbrs_[a-z0-9_]+)\s*\(", header))
-    bound = set(re.findall(r"pub fn (pbrs_[a-z0-9_]+)", open(os.path.join(root, "INTEGRATION.md")).read()))
-    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    bound = dict(re.findall(r"pub fn (pbrs_[a-z0-9_]+)\(([^)]*)\)", rs))
+    assert declared == set(bound), (sorted(declared - set(bound)), sorted(set(bound) - declared))
+    table = dict(K.SCENE_API)
+    table.update(K.PRODUCT_ONLY_API)
+    for name, (_, argtypes) in table.items():
+        n_rs = len([a for a in bound["pbrs_" + name].split(",") if a.strip()])
+        assert n_rs == len(argtypes), f"pbrs_{name}: {n_rs} Rust parameters vs {len(argtypes)} in the ctypes mirror"
+    for cname, ctype in (("pbrs_render_opts", K.RenderOpts), ("pbrs_stats", K.Stats), ("pbrs_scene_info", K.SceneInfo), ("pbrs_material_desc", K.MaterialDesc)):
+        body = re.search(r"pub struct %s \{(.*?)\}" % cname, rs, flags=re.S).group(1)
+        assert re.findall(r"pub (\w+):", body) == [f for f, _ in ctype._fields_], cname
+    # the recorder and the patches name only functions that exist
+    for f in ("gpu_scene.rs", "main_rs.patch", "loader_rs.patch"):
+        text = open(os.path.join(ROOT, "ffi", f)).read()
+        for used in set(re.findall(r"\b(pbrs_[a-z0-9_]+)\s*\(", text)):
+            assert used in declared, f"ffi/{f} calls {used}, which the header does not declare"
+    assert "ffi/pbrs_gpu.rs" in open(os.path.join(ROOT, "INTEGRATION.md")).read()

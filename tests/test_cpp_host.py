@@ -167,3 +167,20 @@ def test_cpp_driver_renders_a_scene_file_like_the_python_path(tmp_path, gpu_api)
     img = film.read_exr(out)
     want, _ = load_pbrt(path).realize(gpu_api).render(integrator="path", msaa=2)
     assert bits_equal(img, want).all()
+
+
+def test_cpp_ply_loader_rejects_counts_that_would_wrap(tmp_path):
+    """A header whose vertex count makes `count * stride * 4` wrap in 64 bits, or whose count has more
+    digits than a long holds, is a load error of the C++ loader -- not a crash."""
+    import re
+    _build()
+    from tests.test_scene_io import write_ply_scene
+    path = write_ply_scene(str(tmp_path))
+    ball = str(tmp_path / "ball.ply")
+    raw = open(ball, "rb").read()
+    for bad in (re.sub(rb"element vertex \d+", b"element vertex 4611686018427387904", raw),
+                re.sub(rb"element face \d+", b"element face 99999999999999999999", raw)):
+        open(ball, "wb").write(bad)
+        r = subprocess.run([CHECK, path, str(tmp_path / "ids.bin")], capture_output=True, text=True)
+        assert r.returncode not in (0, -11, -6, 134, 139), (r.returncode, r.stderr)
+        assert "ply" in (r.stderr + r.stdout).lower()

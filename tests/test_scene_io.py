@@ -1,6 +1,7 @@
 """Either side of the hot path: pbrt-subset scene files in (pbrs_b200/pbrt_loader.py, mirroring
 scene_parser + scene/src/loader.rs) and the EXR film out (pbrs_b200/film.py, src/main.rs:42-53)."""
 import os
+import re
 
 import numpy as np
 import pytest
@@ -157,7 +158,10 @@ def test_ply_reader_matches_the_reference_reader(tmp_path):
     # what the reference cannot read
     raw = open(a, "rb").read()
     for bad in (raw.replace(b"binary_little_endian", b"ascii"), raw.replace(b"ply\n", b"plx\n"), raw[:200],
-                raw.replace(b"property float z", b"property uchar z"), raw.replace(b"element face", b"element fac")):
+                raw.replace(b"property float z", b"property uchar z"), raw.replace(b"element face", b"element fac"),
+                # counts that would wrap the size arithmetic of a 64-bit loader
+                re.sub(rb"element vertex \d+", b"element vertex 4611686018427387904", raw),
+                re.sub(rb"element face \d+", b"element face 99999999999999999999", raw)):
         c = str(tmp_path / "c.ply")
         open(c, "wb").write(bad)
         with pytest.raises(PbrtError):

@@ -1,8 +1,9 @@
 """Top source lines of a kernel in an .ncu-rep captured with --import-source on (-lineinfo build).
-usage: python tools/ncu_lines.py report.ncu-rep [kernel-substring] [top-n]"""
+usage: python tools/ncu_lines.py report.ncu-rep [kernel-substring] [top-n] [launch-index]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else ""; top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+sel = ["--launch-skip", sys.argv[4], "--launch-count", "1"] if len(sys.argv) > 4 else []
+out = subprocess.run(["ncu", "-i", rep] + sel + ["--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = cur_fn = None; hdr = None; agg = {}; tot = {}
 for r in rows:

@@ -58,14 +58,16 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
-def measured_traffic(workload):
-    """DRAM bytes per k_trace<closest> launch from the committed ncu --set full capture of this
-    workload (profiles/r1_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py), or None."""
+def ncu_evidence(workload):
+    """Launch-weighted means of the closest-hit traversal kernel over all bounces of two whole batches,
+    from the committed ncu capture of this workload at this round's kernels (profiles/r2_traffic.json,
+    written from the .ncu-rep by tools/ncu_traffic.py), or {}."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(workload, {}).get("extend_dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            d = json.load(f).get(workload, {})
+        return dict(d.get("extend", {}), source=d.get("source"))
     except Exception:
-        return None
+        return {}
 
 
 def extend_bytes(st):
@@ -321,6 +323,11 @@ def main():
         n_launch = max(1, st_time["launches_extend"])
         ext_ms = st_time["ms_extend"]
         achieved = ext_b / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        ev = ncu_evidence(args.workload) if args.frame_scale == 1.0 else {}
+        limiter = "not profiled for this workload"
+        if ev:
+            limiter = (f"issue slots and L1/L2 latency, not DRAM (ncu: DRAM at {ev.get('dram_pct_of_peak', 0):.1f} % of peak, issue slots {ev.get('issue_active_pct', 0):.0f} % busy, "
+                       f"{ev.get('lanes_per_inst', 0):.1f} of 32 lanes per instruction, {ev.get('occupancy_pct', 0):.0f} % occupancy)")
         sh_ms = st_time["ms_shadow"]
         line = {
             "metric": METRIC, "value": n_samples / (ms_step * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -340,11 +347,17 @@ def main():
                                                               else "render_sharded: NCCL reduce -> one copy out")},
             "gpu_launches": int(st_time["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS/BLAS walk)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": measured_traffic(args.workload) if args.frame_scale == 1.0 else None,
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": ev.get("dram_bytes_per_launch"), "limiter": limiter,
+                         "l2_bytes_per_launch": ev.get("l2_bytes_per_launch"), "local_mem_bytes_per_launch": ev.get("local_mem_bytes_per_launch"),
+                         "lanes_per_instruction": ev.get("lanes_per_inst"), "occupancy_pct": ev.get("occupancy_pct"), "issue_active_pct": ev.get("issue_active_pct"),
+                         "ncu_source": ev.get("source"),
                          "algorithmic_bytes_per_launch": ext_b / n_launch, "ms_per_launch": ext_ms / n_launch, "launches_per_step": int(n_launch),
                          "bytes_per_ray": ext_b / max(1.0, st_count["n_rays_extend"]),
-                         "note": "achieved = algorithmic bytes (SURVEY 8d formula) / summed launch time; traffic = DRAM bytes per launch from ncu "
-                                 "(the BVH is largely L2-resident, so traffic << algorithmic bytes: the kernel is issue-bound, DESIGN.md section 6)"},
+                         "note": "frac = algorithmic bytes (SURVEY 8d formula: 64 B/node, 48 B/triangle, 16 B/sphere, 128 B/instance entry, 64 B/ray) / summed launch "
+                                 "time / the measured HBM copy peak -- the contract's fraction.  traffic, l2_bytes, local_mem_bytes, lanes, occupancy and issue "
+                                 "utilisation are launch-weighted ncu means over all five bounces of two whole batches (profiles/): the BVH is largely "
+                                 "L2-resident, so DRAM traffic << algorithmic bytes and what limits the kernel is `limiter`.  compute-sanitizer is closed on "
+                                 "this pool: memory safety rests on the commit-time depth bound and parity against the oracle"},
             "stages_ms": {k: st_time[k] for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate", "ms_total")},
             "shadow_kernel": {"achieved": shadow_bytes(st_count) / (sh_ms * 1e-3) / 1e9 if sh_ms > 0 else 0.0, "unit": "GB/s"},
             "would_panic": st_count["would_panic"],

@@ -35,7 +35,7 @@ namespace pbrs {
 #define PBRS_TAG_EXIT 0x20000000u     // boundary between the TLAS entries and a mesh walk's
 // Stack entries alive at once: <= one per TLAS level (a pending right child or a COMBINE), the
 // EXIT tag, one far child per BLAS level; commit rejects scenes whose depths do not fit.
-#define PBRS_WALK_STACK 128
+#define PBRS_WALK_STACK PBRS_WALK_STACK_ENTRIES
 #define PBRS_WALK_PARK 16  // words of world-ray state parked beside the stack during a mesh walk
 
 PB_DEV bool ref_advancing(uint32_t n) { return (int32_t)n >= -1; }

@@ -451,6 +451,10 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
 // Each half is well under the instruction-cache footprint and the register count of the one-piece
 // kernel (186 KB of SASS, 128 registers, 4.4 stall cycles per issue waiting for instructions:
 // profiles/r1_final3_ncu_shade_c4.md); the price is 128 bytes of state traffic per path and bounce.
+// Measured (profiles/r2_exp_shade_split.log): shade -11 % on C4, where rebuilding a hit means the
+// triangle's shading record, the normal / uv interpolation and two tangent frames; +12 % on C5 and
+// +18 % on C3, where the hit is a sphere or a small instanced mesh and the record is pure overhead.
+// Commit therefore switches it on per scene (DeviceScene::shade_split: >= 100 000 triangles).
 #ifndef PBRS_SHADE_SPLIT
 #define PBRS_SHADE_SPLIT 1
 #endif
@@ -574,7 +578,7 @@ void launch_shade(const Grid &g, cudaStream_t stream, const DeviceScene &sc, con
     const int *gs = g.shade[INTEGRATOR];
     k_shade<PBRS_CLS_MISS, INTEGRATOR><<<gs[PBRS_CLS_MISS], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
     k_shade<PBRS_CLS_EMISSIVE, INTEGRATOR><<<gs[PBRS_CLS_EMISSIVE], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-    if (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH) {
+    if (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH && sc.shade_split) {
         k_surface<<<g.surface, kThreads, 0, stream>>>(sc, pb, cnt, stage);
         k_scatter<PBRS_CLS_LAMBERT><<<g.scatter[0], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
         k_scatter<PBRS_CLS_MICROFACET><<<g.scatter[1], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
@@ -588,7 +592,7 @@ void launch_shade(const Grid &g, cudaStream_t stream, const DeviceScene &sc, con
 }
 // kernels launched by launch_shade
 template <int INTEGRATOR>
-constexpr int shade_launches() { return (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH) ? PBRS_NUM_CLS + 1 : PBRS_NUM_CLS; }
+int shade_launches(const DeviceScene &sc) { return (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH && sc.shade_split) ? PBRS_NUM_CLS + 1 : PBRS_NUM_CLS; }
 template <int INTEGRATOR>
 void size_shade(Grid &g, int sms);
 
@@ -898,7 +902,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
                 else if (sc.has_ext) k_trace<true, false, true><<<w.grid.shadow_ext, kThreads, 0, stream>>>(sc, pb, q_sh, cnt);
                 else k_trace<true, false, false><<<w.grid.shadow, kThreads, 0, stream>>>(sc, pb, q_sh, cnt);
                 mark(T_SHADOW);
-                launches += (o.integrator == PBRS_INTEGRATOR_PATH ? shade_launches<PBRS_INTEGRATOR_PATH>() : shade_launches<PBRS_INTEGRATOR_DIRECT>()) + 1; ++launches_shadow;
+                launches += (o.integrator == PBRS_INTEGRATOR_PATH ? shade_launches<PBRS_INTEGRATOR_PATH>(sc) : shade_launches<PBRS_INTEGRATOR_DIRECT>(sc)) + 1; ++launches_shadow;
             }
             if (tg.only_sample >= 0) {
                 k_write_ids<<<w.grid.small, kThreads, 0, stream>>>(sc, pb, fp, bp, tg.ids_inst, tg.ids_prim, tg.ids_t);
@@ -955,7 +959,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
                 for (int stage = 0; stage < n_stages; ++stage) {
                     ++launches; ++launches_extend;
                     if (tg.only_sample >= 0) break;
-                    launches += (o.integrator == PBRS_INTEGRATOR_PATH ? shade_launches<PBRS_INTEGRATOR_PATH>() : shade_launches<PBRS_INTEGRATOR_DIRECT>()) + 1; ++launches_shadow;
+                    launches += (o.integrator == PBRS_INTEGRATOR_PATH ? shade_launches<PBRS_INTEGRATOR_PATH>(sc) : shade_launches<PBRS_INTEGRATOR_DIRECT>(sc)) + 1; ++launches_shadow;
                 }
                 if (tg.only_sample >= 0) ++launches;
                 else launches += (tg.film ? 1 : 0) + (tg.samples ? 1 : 0);

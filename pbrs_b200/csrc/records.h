@@ -30,6 +30,8 @@ struct NodeRec {
     uint32_t pad;
 };
 static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
+// Entries of the traversal stack (device_walk.cuh PBRS_WALK_STACK); commit checks the BVH depths against it.
+#define PBRS_WALK_STACK_ENTRIES 128
 #define PBRS_NODE_LEFT_LEAF 4u
 #define PBRS_NODE_RIGHT_LEAF 8u
 #define PBRS_MAX_LEAF_PRIMS 16383u
@@ -236,6 +238,7 @@ struct DeviceScene {
     uint32_t n_instances;
     uint32_t leaf_vote; // lanes waiting at a leaf that end the node phase of the closest-hit walk (kernels.cu)
     uint32_t has_mesh; // any BLAS at all (a scene of spheres skips the cooperative leaf phase)
+    uint32_t shade_split;  // the path integrator shades the heavy classes with k_surface + k_scatter (scenes of big meshes)
     uint32_t coop_closest; // closest-hit walks test their leaf runs cooperatively (scenes with >= 1024 triangles)
     uint32_t has_ext;  // any quad / cuboid / disk instance or sphere BLAS: selects the EXT traversal kernels
 };

@@ -514,6 +514,12 @@ int host_build(SceneImpl &s) {
     s.tlas_root_is_leaf = root.leaf;
     s.tlas_depth = tb.max_depth;
     if (tb.max_depth > 60) { set_error("commit: the TLAS is deeper than 60 levels (traversal stack)"); return PBRS_ERR_UNSUPPORTED; }
+    {   // the walk keeps at most one entry per TLAS level, the EXIT tag and one far child per BLAS level
+        // (device_walk.cuh): with this bound the stack-overflow flag of the kernels is provably dead
+        uint32_t deepest_blas = 0;
+        for (const HostMesh &m : s.meshes) deepest_blas = std::max(deepest_blas, m.depth);
+        if (tb.max_depth + deepest_blas + 2 > PBRS_WALK_STACK_ENTRIES) { set_error("commit: TLAS + BLAS depth exceeds the traversal stack"); return PBRS_ERR_UNSUPPORTED; }
+    }
     // scene/src/lib.rs:54-58: distant lights get half the TLAS diagonal as world radius
     float d[3] = {root.box.mx[0] - root.box.mn[0], root.box.mx[1] - root.box.mn[1], root.box.mx[2] - root.box.mn[2]};
     float half_diag = std::sqrt(v_dot(d, d)) * 0.5f;
@@ -687,6 +693,8 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     ds.has_mesh = s.meshes.empty() ? 0u : 1u;
     ds.coop_closest = f.tris.size() >= 1024 ? 1u : 0u;  // a Cornell box (34 triangles) loses 8 % of its extend time to the bookkeeping
     if (const char *e = std::getenv("PBRS_COOP_CLOSEST")) ds.coop_closest = (uint32_t)std::atoi(e);  // development knob
+    ds.shade_split = f.tris.size() >= 100000 ? 1u : 0u;  // shade -11 % on the 1 M-triangle terrain, +12..18 % on sphere / small-mesh scenes
+    if (const char *e = std::getenv("PBRS_SHADE_SPLIT")) ds.shade_split = (uint32_t)std::atoi(e);
     ds.has_ext = s.simples.empty() ? 0u : 1u;
     for (const HostMesh &m : s.meshes)
         if (!m.balls.empty()) ds.has_ext = 1u;

@@ -9,6 +9,9 @@ Bars (BASELINE.json north_star, DESIGN.md "Parity"):
   * size-independent properties at a full BASELINE config size (tile split = full frame exactly,
     sample split = full frame to summation order, determinism, linearity of the raw sum).
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -17,6 +20,16 @@ from tests.util import SMALL_SCENES, assert_radiance_close, assert_stats_close, 
 
 pytestmark = pytest.mark.gpu
 NAMES = list(SMALL_SCENES)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SAMPLE_OUTLIERS = {}
+
+
+def _pinned_sample_outliers():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "parity_outliers_samples.json")) as f:
+            return json.load(f)
+    except FileNotFoundError:
+        return {}
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -76,6 +89,18 @@ def test_per_sample_radiance_and_counters(oracle_api, gpu_api, name, integrator,
     exact = float(bits_equal(a, b).all(axis=-1).mean())
     print(f"{name} {integrator} d{depth}: {exact * 100:.3f}% of samples bit-identical, {n_bad} beyond 1e-4")
     assert exact > 0.98
+    # the allowance is pinned to what was MEASURED on a B200 (tests/golden/parity_outliers_samples.json,
+    # rewritten into profiles/ with PBRS_WRITE_OUTLIERS=1): the outliers are last-ulp differences between
+    # glibc's float transcendentals and the device's FP64-evaluated ones, so another host libm may move
+    # the count by a few -- twice the measured count plus two is still 10-100x tighter than 0.1 %
+    key = f"{name}/{integrator}/d{depth}"
+    _SAMPLE_OUTLIERS[key] = {"samples": int(a.shape[0] * a.shape[1] * a.shape[2]), "beyond_1e-4": n_bad, "bit_identical_fraction": exact}
+    if os.environ.get("PBRS_WRITE_OUTLIERS"):
+        with open(os.path.join(ROOT, "profiles", "parity_outliers_samples.json"), "w") as f:
+            json.dump(_SAMPLE_OUTLIERS, f, indent=1, sort_keys=True)
+    pinned = _pinned_sample_outliers().get(key)
+    if pinned is not None:
+        assert n_bad <= 2 * pinned["beyond_1e-4"] + 2, f"{key}: {n_bad} samples beyond 1e-4, measured {pinned['beyond_1e-4']} when pinned"
     assert_stats_close(sb, sa, f"{name} {integrator} depth {depth}")
     assert sb["launches"] > 0 and sb["launches_extend"] > 0
 
@@ -230,3 +255,25 @@ def test_instanced_walk_matches_oracle(oracle_api, gpu_api):
     fb, sb = hg.render(integrator="path", msaa=1, max_depth=3, flags=1)
     assert_radiance_close(fb, fa, "field film", outliers=1e-3)
     assert_stats_close(sb, sa, "field film", rel=1e-3)
+
+
+@pytest.mark.parametrize("name", ["terrain", "zoo_image", "field", "preset_everything"])
+def test_per_scene_kernel_switches_do_not_change_the_film(gpu_api, name, monkeypatch):
+    """Commit picks per scene between the one-piece and the split (surface + scatter) shade kernels
+    and between the sequential and the cooperative closest-hit leaf phase (DeviceScene::shade_split,
+    ::coop_closest: scene-size heuristics).  Both choices are scheduling only: forced either way,
+    the film is bit-identical and the counters are equal."""
+    sd = SMALL_SCENES[name]()
+    ref = None
+    for split, coop in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        monkeypatch.setenv("PBRS_SHADE_SPLIT", str(split))
+        monkeypatch.setenv("PBRS_COOP_CLOSEST", str(coop))
+        h = sd.realize(gpu_api)
+        film, st = h.render(integrator="path", msaa=2, max_depth=5, flags=1)
+        # (would_panic counts threads that saw an assert, per kernel: the KINDS are scheduling-independent, the counts are not)
+        key = (st["n_samples"], st["n_rays_extend"], st["n_rays_shadow"], st["n_nodes"], st["n_tris"], st["n_spheres"], st["n_instances"], tuple(sorted(st["would_panic"])))
+        if ref is None:
+            ref = (film, key)
+        else:
+            assert bits_equal(film, ref[0]).all(), (name, split, coop, int((~bits_equal(film, ref[0])).sum()))
+            assert key == ref[1], (name, split, coop, key, ref[1])

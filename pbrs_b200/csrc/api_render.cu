@@ -239,10 +239,16 @@ int pbrs_render(const pbrs_scene *s, const pbrs_render_opts *o, float *out_rgb, 
     if (rc < 0) return rc;
     RenderTargets tg;
     tg.film = impl.film;
+    tg.host_film = out_rgb;
     rc = render_frame(impl, impl, *o, tg, nullptr, st);
     if (rc < 0) return rc;
-    rc = film_to_host(impl, impl, *o, out_rgb);
-    if (rc < 0) return rc;
+    if (tg.host_copied) {  // the bands went home batch by batch: wait for the last one
+        cudaError_t e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "film copy");
+    } else {
+        rc = film_to_host(impl, impl, *o, out_rgb);
+        if (rc < 0) return rc;
+    }
     return check_last_frame(impl);
 }
 

@@ -817,7 +817,28 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
     const uint64_t total_paths = total_pixels * fp.spp_r;
     if (total_paths < capacity) capacity = (uint32_t)std::max<uint64_t>(total_paths, 32);
     if (capacity < fp.spp_r) capacity = fp.spp_r;
-    const uint32_t ppb = std::max<uint32_t>(1u, capacity / std::max(fp.spp_r, 1u));  // pixels per batch
+
+    uint32_t ppb = std::max<uint32_t>(1u, capacity / std::max(fp.spp_r, 1u));  // pixels per batch
+    // End-to-end path (pbrs_render into a page-locked film, whole frame, no tile split): batches of
+    // whole tile rows are contiguous row bands of the film, so each batch's band goes home on its own
+    // lane stream as soon as it is accumulated -- the copy overlaps the other lane's kernels.  A frame
+    // that would fit one batch is cut in up to four, else the copy could not overlap anything.
+    tg.host_copied = false;
+    bool band_copies = false;
+    {
+        const bool whole = o.crop_w == 0 || o.crop_h == 0;
+        const bool tile_split_now = o.world_size > 1 && o.split == PBRS_SPLIT_TILES;
+        cudaPointerAttributes pa;
+        const bool pinned = tg.host_film && cudaPointerGetAttributes(&pa, tg.host_film) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        static const bool env_no_bands = std::getenv("PBRS_NO_BAND_COPIES") != nullptr;  // development knob for A/B runs
+        if (pinned && whole && !tile_split_now && tg.film && fp.spp_r > 0 && !env_no_bands) {
+            const uint32_t tiles_x = (W + 63) / 64, tiles_y = (H + 63) / 64, row_px = tiles_x * 4096u;
+            uint32_t rows_per_batch = ppb / row_px;
+            if (rows_per_batch >= tiles_y && tiles_y >= 2) rows_per_batch = (tiles_y + std::min(4u, tiles_y) - 1) / std::min(4u, tiles_y);
+            if (rows_per_batch >= 1) { ppb = rows_per_batch * row_px; band_copies = true; }
+        }
+    }
     const uint32_t n_batches = fp.spp_r == 0 ? 0 : (uint32_t)((total_pixels + ppb - 1) / ppb);
 
     const bool count_trav = (o.flags & PBRS_FLAG_COUNT_TRAVERSAL) != 0;
@@ -909,6 +930,12 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
                 ++launches;
             } else {
                 if (tg.film) { k_accumulate<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.film); ++launches; mark(T_ACC); }
+                if (band_copies) {  // this batch's tile rows are rows [y0, y1) of the film, full width: one contiguous copy
+                    const uint32_t row_px = ((W + 63) / 64) * 4096u;
+                    const uint32_t y0 = (bp.first_pixel / row_px) * 64u, y1 = std::min(H, ((bp.first_pixel + bp.n_pixels) / row_px) * 64u);
+                    const size_t off = 3 * (size_t)W * y0;
+                    if (y1 > y0) CK(cudaMemcpyAsync(tg.host_film + off, tg.film + off, sizeof(float) * 3 * (size_t)W * (y1 - y0), cudaMemcpyDeviceToHost, stream));
+                }
                 if (tg.samples) { k_write_samples<<<w.grid.small, kThreads, 0, stream>>>(pb, fp, bp, tg.samples); ++launches; mark(T_ACC); }
             }
         }
@@ -932,8 +959,8 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
         fpk.flags = fp.flags; fpk.x0 = fp.x0; fpk.y0 = fp.y0; fpk.x1 = fp.x1; fpk.y1 = fp.y1; fpk.width = fp.width; fpk.height = fp.height;
         fpk.tiles = fp.tiles; fpk.n_tiles = fp.n_tiles;
         put(shape, sizeof shape); put(&fpk, sizeof fpk); put(&total_pixels, sizeof total_pixels);
-        const void *ptrs[12] = {tg.film, tg.samples, tg.ids_inst, tg.ids_prim, tg.ids_t, w.slab[0], w.slab[1], w.counts, w.stats, w.tiles,
-                                r.dscene.tlas_nodes, r.dscene.inst_trav};
+        const void *ptrs[13] = {tg.film, tg.samples, tg.ids_inst, tg.ids_prim, tg.ids_t, w.slab[0], w.slab[1], w.counts, w.stats, w.tiles,
+                                r.dscene.tlas_nodes, r.dscene.inst_trav, band_copies ? tg.host_film : nullptr};
         put(ptrs, sizeof ptrs);
         if (!w.graph_exec || key != w.graph_key) {
             if (w.graph_exec) { cudaGraphExecDestroy(w.graph_exec); w.graph_exec = nullptr; }
@@ -972,6 +999,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
     }
     stream = caller_stream;
     CK(cudaGetLastError());
+    tg.host_copied = band_copies;
     if (want_stats) {
         CK(cudaEventRecord(w.ev[1], stream));
         CK(cudaEventSynchronize(w.ev[1]));

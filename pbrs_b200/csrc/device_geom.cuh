@@ -35,6 +35,23 @@ PB_DEV f4 ld16(const void *p) {
     f4 r; memcpy(&r, p, 16); return r;
 #endif
 }
+// 32-byte read-only load of a 32-byte aligned half record (LDG.E.256.CONSTANT, new with sm_100): a
+// 64-byte node / triangle / instance record is two requests to the L1 instead of four -- the
+// traversal kernels are bound by the L1's load pipe (ncu: l1tex data-pipe wavefronts 74 % of peak)
+#ifndef PBRS_LD256
+#define PBRS_LD256 1
+#endif
+
+PB_DEV void ld32(const void *p, f4 &a, f4 &b) {
+#if defined(__CUDA_ARCH__) && PBRS_LD256
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+#else
+    a = ld16(p);
+    b = ld16(reinterpret_cast<const char *>(p) + 16);
+#endif
+}
 PB_DEV uint32_t ld_u32(const uint32_t *p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);
@@ -134,9 +151,14 @@ struct TriVerts {
     vec3 p0, p1, p2, n;
     uint32_t orig, flags;
 };
+// (WIDE = two 32-byte loads: the traversal kernels only -- ptxas 12.9 crashes on the 256-bit load
+// inside the out-of-line functions of the shade kernels)
+template <bool WIDE = false>
 PB_DEV TriVerts load_tri(const TriRec *t) {
     const char *b = reinterpret_cast<const char *>(t);
-    f4 a = ld16(b), c = ld16(b + 16), d = ld16(b + 32), e = ld16(b + 48);
+    f4 a, c, d, e;
+    if constexpr (WIDE) { ld32(b, a, c); ld32(b + 32, d, e); }
+    else { a = ld16(b); c = ld16(b + 16); d = ld16(b + 32); e = ld16(b + 48); }
     TriVerts v;
     v.p0 = mk(a.x, a.y, a.z); v.orig = f2u(a.w);
     v.p1 = mk(c.x, c.y, c.z); v.flags = f2u(c.w);
@@ -330,9 +352,12 @@ PB_DEV bool sphere_intersect(vec3 c, float radius, const Ray &r, Isect &out, Dia
 // ---------------------------------------------------------------------------------------------
 PB_DEV float row_pt(f4 m, vec3 p) { return m.x * p.x + m.y * p.y + m.z * p.z + m.w * 1.0f; }
 PB_DEV float row_vec(f4 m, vec3 v) { return m.x * v.x + m.y * v.y + m.z * v.z + m.w * 0.0f; }
+template <bool WIDE = false>
 PB_DEV Ray to_object(const InstTravRec *it, const Ray &r, uint32_t &shape_kind, uint32_t &shape_index) {
     const char *b = reinterpret_cast<const char *>(it);
-    f4 r0 = ld16(b), r1 = ld16(b + 16), r2 = ld16(b + 32), tail = ld16(b + 48);
+    f4 r0, r1, r2, tail;
+    if constexpr (WIDE) { ld32(b, r0, r1); ld32(b + 32, r2, tail); }
+    else { r0 = ld16(b); r1 = ld16(b + 16); r2 = ld16(b + 32); tail = ld16(b + 48); }
     shape_kind = f2u(tail.x);
     shape_index = f2u(tail.y);
     Ray o;

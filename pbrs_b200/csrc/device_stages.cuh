@@ -181,9 +181,9 @@ PB_DEV uint32_t hit_class(const DeviceScene &sc, const Hit &h) {
 }
 template <bool COUNT>
 PB_DEV void stage_extend(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
-    uint32_t st_ref[PBRS_WALK_STACK], st_park[PBRS_WALK_PARK];
-    float st_tl[PBRS_WALK_STACK];
-    Walk<false, COUNT, true, ArrayStack<false>> w(ArrayStack<false>(st_ref, st_tl, st_park));
+    StackPair st_ent[PBRS_WALK_STACK];
+    alignas(16) uint32_t st_park[PBRS_WALK_PARK];
+    Walk<false, COUNT, true, ArrayStack<false>> w(ArrayStack<false>(st_ent, st_park));
     w.run(sc, load_ray(pb, j), dg, tc);
     store_hit(pb, j, w.best);
 }
@@ -626,12 +626,12 @@ PB_DEV void shadow_finish(const PathBuffers &pb, uint32_t j, uint32_t vis) {
 template <bool COUNT>
 PB_DEV void stage_shadow(const DeviceScene &sc, const PathBuffers &pb, uint32_t j, Diag &dg, TravCount &tc) {
     uint32_t vis = 0u;
-    uint32_t st_ref[PBRS_WALK_STACK], st_park[PBRS_WALK_PARK];
-    float st_tl[1];
+    uint32_t st_ref[PBRS_WALK_STACK];
+    alignas(16) uint32_t st_park[PBRS_WALK_PARK];
     for (int which = 0; which < 2; ++which) {
         Ray r;
         if (!shadow_ray(pb, j, which, r)) continue;
-        Walk<true, COUNT, true, ArrayStack<true>> w(ArrayStack<true>(st_ref, st_tl, st_park));
+        Walk<true, COUNT, true, ArrayStack<true>> w(ArrayStack<true>(st_ref, st_park));
         w.run(sc, r, dg, tc);
         if (!w.occluded) vis |= 1u << which;
     }

@@ -24,6 +24,8 @@
 // cases and hands everything within a few ulps of the boundary to the exact divisions, so the
 // pass/fail outcome of every box is bit-identical to the reference's.
 #pragma once
+#include <type_traits>
+
 #include "device_geom.cuh"
 #include "device_simple.cuh"
 
@@ -149,22 +151,31 @@ PB_DEV int retest(float tl, float t_max, float c0) {
     return -1;
 }
 
-// The walk's stack in plain arrays (host build, sequential callers); the traversal kernels use a
-// shared-memory ring with the same interface (kernels.cu SmemStack).  Closest-hit entries are
-// (link, t_low) pairs, any-hit entries bare links; `park` is PBRS_WALK_PARK words beside the stack.
+// The walk's stack in a plain array (local memory in the traversal kernels; the shared-memory ring
+// of kernels.cu has the same interface).  A closest-hit entry is one 8-byte (link, t_low) pair --
+// one local load / store per pop / push instead of two: local-memory requests outnumber the
+// global ones 2.7 : 1 in the closest-hit kernel (ncu r2) -- an any-hit entry a bare link; `park` is
+// PBRS_WALK_PARK words beside the stack.
+struct alignas(16) ParkVec {
+    uint32_t x, y, z, w;
+};
+struct alignas(8) StackPair {
+    uint32_t ref;
+    float tl;
+};
 template <bool ANY>
 struct ArrayStack {
-    uint32_t *ref;
-    float *tl;
+    using Entry = typename std::conditional<ANY, uint32_t, StackPair>::type;
+    Entry *ent;
     uint32_t *park;
     int sp;
-    PB_DEV ArrayStack(uint32_t *r, float *t, uint32_t *p) : ref(r), tl(t), park(p), sp(0) {}
+    PB_DEV ArrayStack(Entry *e, uint32_t *p) : ent(e), park(p), sp(0) {}
     PB_DEV void reset() { sp = 0; }
     PB_DEV bool empty() const { return sp == 0; }
     PB_DEV void push(uint32_t r, float t, Diag &dg) {
         if (sp < PBRS_WALK_STACK) {
-            ref[sp] = r;
-            if (!ANY) tl[sp] = t;
+            if constexpr (ANY) ent[sp] = r;
+            else { StackPair e; e.ref = r; e.tl = t; ent[sp] = e; }
             ++sp;
         } else {
             flag(dg, P_STACK);
@@ -172,11 +183,19 @@ struct ArrayStack {
     }
     PB_DEV void pop(uint32_t &r, float &t) {
         --sp;
-        r = ref[sp];
-        t = ANY ? 0.0f : tl[sp];
+        if constexpr (ANY) { r = ent[sp]; t = 0.0f; }
+        else { const StackPair e = ent[sp]; r = e.ref; t = e.tl; }
     }
-    PB_DEV void park_set(int k, uint32_t v) { park[k] = v; }
-    PB_DEV uint32_t park_get(int k) const { return park[k]; }
+    // the park words, four at a time (16-byte aligned: one local-memory request instead of four)
+    PB_DEV void park_set4(int q, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        ParkVec v; v.x = a; v.y = b; v.z = c; v.w = d;
+        reinterpret_cast<ParkVec *>(park)[q] = v;
+    }
+    PB_DEV u4 park_get4(int q) const {
+        const ParkVec v = reinterpret_cast<const ParkVec *>(park)[q];
+        u4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+        return r;
+    }
 };
 
 // EXT = the scene holds quads / cuboids / disks / isolated triangles, a sphere BLAS, or a triangle
@@ -240,22 +259,27 @@ struct Walk {
     // World-ray state parked for the duration of a mesh walk (restored bit for bit; three IEEE
     // divisions for rd at 3 of 32 lanes cost more than three loads, ncu r2).
     PB_DEV void save_world() {
-        st.park_set(0, f2u(o.x)); st.park_set(1, f2u(o.y)); st.park_set(2, f2u(o.z));
-        st.park_set(3, f2u(d.x)); st.park_set(4, f2u(d.y)); st.park_set(5, f2u(d.z));
-        st.park_set(6, f2u(t_max));
-        st.park_set(7, f2u(rd.x)); st.park_set(8, f2u(rd.y)); st.park_set(9, f2u(rd.z)); st.park_set(10, bits);
-        if (!ANY) { st.park_set(11, f2u(best.t)); st.park_set(12, best.inst); st.park_set(13, best.tri); st.park_set(14, cur_inst); }
+        st.park_set4(0, f2u(o.x), f2u(o.y), f2u(o.z), f2u(t_max));
+        st.park_set4(1, f2u(d.x), f2u(d.y), f2u(d.z), bits);
+        if (ANY) st.park_set4(2, f2u(rd.x), f2u(rd.y), f2u(rd.z), 0u);
+        else {
+            st.park_set4(2, f2u(rd.x), f2u(rd.y), f2u(rd.z), cur_inst);
+            st.park_set4(3, f2u(best.t), best.inst, best.tri, 0u);
+        }
     }
     PB_DEV void restore_world() {
-        o = mk(u2f(st.park_get(0)), u2f(st.park_get(1)), u2f(st.park_get(2)));
-        d = mk(u2f(st.park_get(3)), u2f(st.park_get(4)), u2f(st.park_get(5)));
-        t_max = u2f(st.park_get(6));
-        rd = mk(u2f(st.park_get(7)), u2f(st.park_get(8)), u2f(st.park_get(9)));
-        bits = st.park_get(10);
+        const u4 a = st.park_get4(0), b = st.park_get4(1), c = st.park_get4(2);
+        o = mk(u2f(a.x), u2f(a.y), u2f(a.z)); t_max = u2f(a.w);
+        d = mk(u2f(b.x), u2f(b.y), u2f(b.z)); bits = b.w;
+        rd = mk(u2f(c.x), u2f(c.y), u2f(c.z));
 #if PBRS_BOX_FMA
         set_fma_terms();
 #endif
-        if (!ANY) { best.t = u2f(st.park_get(11)); best.inst = st.park_get(12); best.tri = st.park_get(13); cur_inst = st.park_get(14); }
+        if (!ANY) {
+            const u4 e = st.park_get4(3);
+            cur_inst = c.w;
+            best.t = u2f(e.x); best.inst = e.y; best.tri = e.z;
+        }
     }
     // exact pass of the stacked child `ref` (the rare re-test): its box is in its parent's record
     PB_DEV bool exact_child(const DeviceScene &sc, uint32_t ref, float extent) const {
@@ -295,7 +319,8 @@ struct Walk {
     PB_DEV void expand(const DeviceScene &sc, Diag &dg, TravCount &tc) {
         if (COUNT) tc.nodes++;
         const char *b = reinterpret_cast<const char *>(nodes + next);
-        f4 q0 = ld16(b), q1 = ld16(b + 16), q2 = ld16(b + 32), q3 = ld16(b + 48);
+        f4 q0, q1, q2, q3;
+        ld32(b, q0, q1); ld32(b + 32, q2, q3);
 #if PBRS_BOX_FMA
         const PairTest pt = test_pair(q0, q1, q2, o, d, rd, nord, c0, fast(), t_max, !ANY && !in_mesh());
 #else
@@ -349,7 +374,7 @@ struct Walk {
             Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
             uint32_t s = tri_base + first;
             while (true) {
-                TriVerts tv = load_tri(sc.tris + s);
+                TriVerts tv = load_tri<true>(sc.tris + s);
                 if (EXT && (tv.flags & PBRS_TRI_SPHERE)) {
                     // IsoBlas<Sphere>: the leaf closure is the sphere's own test (blas.rs:267-274)
                     if (COUNT) tc.spheres++;
@@ -379,7 +404,7 @@ struct Walk {
         if (COUNT) tc.insts++;
         Ray wr; wr.o = o; wr.d = d; wr.t_max = t_max;
         uint32_t kind, index;
-        Ray obj = to_object(sc.inst_trav + first, wr, kind, index);
+        Ray obj = to_object<true>(sc.inst_trav + first, wr, kind, index);
         if (!(len2(obj.d) > (ANY ? 1e-6f : 1e-3f))) flag(dg, P_MISC);
         if (kind != PBRS_SHAPE_MESH) {
             float t = PB_INF;

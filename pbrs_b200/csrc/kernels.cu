@@ -118,6 +118,24 @@ template <bool ANY> constexpr int kRefillIdleLanes = ANY ? PBRS_REFILL_IDLE_LANE
 #ifndef PBRS_COOP_ANY
 #define PBRS_COOP_ANY 1
 #endif
+#ifndef PBRS_COOP_FILL_SERIAL
+#define PBRS_COOP_FILL_SERIAL 0  // 1: every owner writes all its (lane, triangle) slots one by one (the first version: 5 % of the kernel's instructions at 4 of 32 lanes)
+#endif
+// Deferred unwinds: a lane whose walk ran dry waits for the end of the round and pops together with
+// the others instead of alone, right away (a pop runs at 3-5 of 32 lanes and is two dependent
+// local-memory accesses).  Any-hit walks gain (shadow -5 % on C4, -6 % on C5 with 2 node steps per
+// round); closest-hit walks do not (C4 equal, C3 / C1 +6-10 %): profiles/r2_exp_ld256_packed_stack_defer.log
+#ifndef PBRS_DEFER_UNWIND_ANY
+#define PBRS_DEFER_UNWIND_ANY 1
+#endif
+#ifndef PBRS_DEFER_UNWIND_CLOSEST
+#define PBRS_DEFER_UNWIND_CLOSEST 0
+#endif
+#ifndef PBRS_NODE_STEPS_ANY
+#define PBRS_NODE_STEPS_ANY 2
+#endif
+template <bool ANY> constexpr bool kDeferUnwind = ANY ? (PBRS_DEFER_UNWIND_ANY != 0) : (PBRS_DEFER_UNWIND_CLOSEST != 0);
+template <bool ANY> constexpr int kNodeSteps = ANY ? PBRS_NODE_STEPS_ANY : PBRS_NODE_STEPS;
 #ifndef PBRS_COOP_CLOSEST
 #define PBRS_COOP_CLOSEST 1  // with the stack in local memory: extend -4.5 % on C4 and C5; scenes of a few triangles lose 8 % and switch it off (DeviceScene::coop_closest)
 #endif
@@ -199,8 +217,15 @@ struct SmemStack {
             lo = sp;
         }
     }
-    __device__ __forceinline__ void park_set(int k, uint32_t v) { spill_ref[PBRS_WALK_STACK + k] = v; }
-    __device__ __forceinline__ uint32_t park_get(int k) const { return spill_ref[PBRS_WALK_STACK + k]; }
+    __device__ __forceinline__ void park_set4(int q, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        uint32_t *p = spill_ref + PBRS_WALK_STACK + 4 * q;
+        p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+    }
+    __device__ __forceinline__ u4 park_get4(int q) const {
+        const uint32_t *p = spill_ref + PBRS_WALK_STACK + 4 * q;
+        u4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3];
+        return v;
+    }
 };
 
 template <bool ANY, bool COUNT, bool EXT>
@@ -212,15 +237,16 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
     const uint32_t n = *count;
     // local memory: the spill area of the stack + the park slots (one array, dynamically indexed, so
     // that the statically indexed park slots are not promoted to registers)
+#if PBRS_SMEM_STACK
     uint32_t st_ref[PBRS_WALK_STACK + PBRS_WALK_PARK];
     float st_tl[ANY ? 1 : PBRS_WALK_STACK];
-#if PBRS_SMEM_STACK
     using Stk = SmemStack<ANY>;
     __shared__ typename Stk::Entry ring_mem[Stk::S * kThreads];
     Walk<ANY, COUNT, EXT, Stk> w(Stk(ring_mem + threadIdx.x, st_ref, st_tl));
 #else
     using Stk = ArrayStack<ANY>;
-    Walk<ANY, COUNT, EXT, Stk> w(Stk(st_ref, st_tl, st_ref + PBRS_WALK_STACK));
+    alignas(16) typename Stk::Entry st_mem[PBRS_WALK_STACK + PBRS_WALK_PARK];  // (closest-hit: the park words take half of their 16 entries)
+    Walk<ANY, COUNT, EXT, Stk> w(Stk(st_mem, reinterpret_cast<uint32_t *>(st_mem + PBRS_WALK_STACK)));
 #endif
     // the warp's chunk of the queue: [chunk[0], chunk[1]) is still to be handed out
     __shared__ uint32_t chunk_mem[kThreads / 32][2];
@@ -274,9 +300,18 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
             if (m_adv == 0u || __popc(m_leaf) >= vote) break;
             // (a real loop: three unrolled copies of the step push the kernel past 50 KB of SASS and the
             // extend time up 10 %, profiles/r2_exp_shade_phased_and_code_size.log)
+            if constexpr (kDeferUnwind<ANY>) {
+                // dead ends are not unwound one lane at a time: every lane that ran dry (left a leaf, or
+                // both children failed) pops at the top of the next round, together with the others
+                if (w.next == PBRS_NONE) w.unwind(sc, dg);
 #pragma unroll 1
-            for (int k = 0; k < PBRS_NODE_STEPS; ++k)
-                if (w.advancing()) w.advance(sc, dg, tc);
+                for (int k = 0; k < kNodeSteps<ANY>; ++k)
+                    if ((int32_t)w.next >= 0) w.expand(sc, dg, tc);
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < kNodeSteps<ANY>; ++k)
+                    if (w.advancing()) w.advance(sc, dg, tc);
+            }
         }
         __syncwarp();
 #if PBRS_COOP_ANY
@@ -302,12 +337,24 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 }
                 const uint32_t excl = incl - c;
                 const bool in_pass = mine && incl <= 32u;  // the first owner always fits (c <= 6)
+#if PBRS_COOP_FILL_SERIAL
                 if (in_pass)
                     for (uint32_t k = 0; k < c; ++k) slot[excl + k] = (uint8_t)(lane_id() | (k << 5));
                 const uint32_t total = __reduce_max_sync(0xFFFFFFFFu, in_pass ? incl : 0u);
                 __syncwarp();
                 const bool work = lane_id() < total;
                 const uint32_t e = work ? slot[lane_id()] : 0u;
+#else
+                // slot p = first pair of a run: its owner leaves its lane there (one store); a working
+                // lane finds the start of its run as the highest start bit at or below its own index
+                const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, in_pass ? (1u << excl) : 0u);
+                if (in_pass) slot[excl] = (uint8_t)lane_id();
+                const uint32_t total = __reduce_max_sync(0xFFFFFFFFu, in_pass ? incl : 0u);
+                __syncwarp();
+                const bool work = lane_id() < total;
+                const uint32_t p0 = 31u - (uint32_t)__clz((int)(starts & (0xFFFFFFFFu >> (31u - lane_id()))));
+                const uint32_t e = work ? ((uint32_t)slot[p0 & 31u] | ((lane_id() - p0) << 5)) : 0u;
+#endif
                 const int src = (int)(e & 31u);
                 Ray r;
                 r.o.x = __shfl_sync(0xFFFFFFFFu, w.o.x, src); r.o.y = __shfl_sync(0xFFFFFFFFu, w.o.y, src); r.o.z = __shfl_sync(0xFFFFFFFFu, w.o.z, src);
@@ -316,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 const uint32_t first = __shfl_sync(0xFFFFFFFFu, w.tri_base + (w.next & PBRS_LEAF_FIRST_MASK), src);
                 bool hit = false;
                 if (work) {
-                    const TriVerts tv = load_tri(sc.tris + first + (e >> 5));
+                    const TriVerts tv = load_tri<true>(sc.tris + first + (e >> 5));
                     if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { float t; hit = ball_test(tv.p0, tv.p1.x, r, true, t, dg); }
                     else hit = mesh_tri_occludes(tv, r, dg);
                 }
@@ -354,12 +401,23 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 }
                 const uint32_t excl = incl - c;
                 const bool in_pass = mine && incl <= 32u;  // the first owner always fits (c <= 6)
+#if PBRS_COOP_FILL_SERIAL
                 if (in_pass)
                     for (uint32_t k = 0; k < c; ++k) slot[excl + k] = (uint16_t)(lane_id() | (k << 5) | (c << 8));
                 const uint32_t total = __reduce_max_sync(0xFFFFFFFFu, in_pass ? incl : 0u);
                 __syncwarp();
                 const bool work = lane_id() < total;
                 const uint32_t e = work ? slot[lane_id()] : 0u;
+#else
+                const unsigned starts = __reduce_or_sync(0xFFFFFFFFu, in_pass ? (1u << excl) : 0u);
+                if (in_pass) slot[excl] = (uint16_t)(lane_id() | (c << 8));
+                const uint32_t total = __reduce_max_sync(0xFFFFFFFFu, in_pass ? incl : 0u);
+                __syncwarp();
+                const bool work = lane_id() < total;
+                const uint32_t p0 = 31u - (uint32_t)__clz((int)(starts & (0xFFFFFFFFu >> (31u - lane_id()))));
+                const uint32_t e0 = work ? (uint32_t)slot[p0 & 31u] : 0u;
+                const uint32_t e = work ? ((e0 & 31u) | ((lane_id() - p0) << 5) | (e0 & 0xFF00u)) : 0u;
+#endif
                 const int src = (int)(e & 31u);
                 const uint32_t k = (e >> 5) & 7u, run = e >> 8;
                 Ray r;
@@ -370,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
                 float val = PB_INF;
                 if (work) {
                     const uint32_t s = first + k;
-                    const TriVerts tv = load_tri(sc.tris + s);
+                    const TriVerts tv = load_tri<true>(sc.tris + s);
                     float t;
                     bool hit;
                     if (EXT && (tv.flags & PBRS_TRI_SPHERE)) { if (COUNT) tc.spheres++; hit = ball_test(tv.p0, tv.p1.x, r, false, t, dg); }

@@ -151,7 +151,7 @@ template <bool ANY> constexpr int kNodeSteps = ANY ? PBRS_NODE_STEPS_ANY : PBRS_
 // r2_exp_stack_prefetch_steps.log): the ring costs more than it saves -- extend +3.4 % on C4, +4.7 % on
 // C5, +6 % on C3 against the same walk with its stack in local memory, and a ring of 4 entries is worse
 // than one of 8.  Local-memory stack traffic is 2.6 % of the instructions and hits L1 88 % of the time
-// (ncu, profiles/r2_stack_counters.md); the ring adds its full / empty bookkeeping to every push and
+// (ncu before the change, profiles/r2_ncu_trace_c4.md); the ring adds its full / empty bookkeeping to every push and
 // pop.  It therefore stays a build option (-DPBRS_SMEM_STACK=1) and the default stack is local memory.
 #ifndef PBRS_SMEM_STACK
 #define PBRS_SMEM_STACK 0

@@ -326,8 +326,14 @@ def main():
         ev = ncu_evidence(args.workload) if args.frame_scale == 1.0 else {}
         limiter = "not profiled for this workload"
         if ev:
-            limiter = (f"issue slots and L1/L2 latency, not DRAM (ncu: DRAM at {ev.get('dram_pct_of_peak', 0):.1f} % of peak, issue slots {ev.get('issue_active_pct', 0):.0f} % busy, "
+            limiter = (f"the SM's L1 load pipe, issue slots and SIMT efficiency, not DRAM (ncu: L1 data-pipe wavefronts {ev.get('l1_pipe_pct', 0):.0f} % of peak, DRAM at "
+                       f"{ev.get('dram_pct_of_peak', 0):.1f} % of peak, issue slots {ev.get('issue_active_pct', 0):.0f} % busy, "
                        f"{ev.get('lanes_per_inst', 0):.1f} of 32 lanes per instruction, {ev.get('occupancy_pct', 0):.0f} % occupancy)")
+        # thread instructions per ray of the closest-hit walk: ncu's instruction rate (warp instructions x lanes per millisecond of kernel
+        # time, launch-weighted over two whole batches) x this run's kernel time per ray
+        thread_inst_per_ray = None
+        if ev.get("warp_inst_per_launch") and ev.get("lanes_per_inst") and ev.get("ms_per_launch") and st_count["n_rays_extend"]:
+            thread_inst_per_ray = ev["warp_inst_per_launch"] * ev["lanes_per_inst"] / ev["ms_per_launch"] * ext_ms / st_count["n_rays_extend"]
         sh_ms = st_time["ms_shadow"]
         line = {
             "metric": METRIC, "value": n_samples / (ms_step * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -350,6 +356,7 @@ def main():
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": ev.get("dram_bytes_per_launch"), "limiter": limiter,
                          "l2_bytes_per_launch": ev.get("l2_bytes_per_launch"), "local_mem_bytes_per_launch": ev.get("local_mem_bytes_per_launch"),
                          "lanes_per_instruction": ev.get("lanes_per_inst"), "occupancy_pct": ev.get("occupancy_pct"), "issue_active_pct": ev.get("issue_active_pct"),
+                         "l1_data_pipe_pct": ev.get("l1_pipe_pct"), "thread_instructions_per_ray": thread_inst_per_ray,
                          "ncu_source": ev.get("source"),
                          "algorithmic_bytes_per_launch": ext_b / n_launch, "ms_per_launch": ext_ms / n_launch, "launches_per_step": int(n_launch),
                          "bytes_per_ray": ext_b / max(1.0, st_count["n_rays_extend"]),

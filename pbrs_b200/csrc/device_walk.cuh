@@ -365,6 +365,36 @@ struct Walk {
         else { next = PBRS_NONE; ret = PB_INF; }
     }
 
+    // One leaf run of a mesh, from record `s` to the first one flagged LAST_IN_LEAF, against `ray`
+    // (shape/src/blas.rs:447-454).  Closest-hit: the running (bt, btri) of the mesh walk is improved
+    // by strictly smaller hits; any-hit: returns true at the first occluder.
+    PB_DEV bool run_tris(const DeviceScene &sc, uint32_t s, const Ray &ray, float &bt, uint32_t &btri, Diag &dg, TravCount &tc) const {
+        while (true) {
+            TriVerts tv = load_tri<true>(sc.tris + s);
+            if (EXT && (tv.flags & PBRS_TRI_SPHERE)) {
+                // IsoBlas<Sphere>: the leaf closure is the sphere's own test (blas.rs:267-274)
+                if (COUNT) tc.spheres++;
+                float t;
+                if (ball_test(tv.p0, tv.p1.x, ray, ANY, t, dg)) {
+                    if (ANY) return true;
+                    if (t < bt) { bt = t; btri = s; }
+                }
+            } else if (ANY) {
+                if (COUNT) tc.tris++;
+                if (mesh_tri_occludes(tv, ray, dg)) return true;
+            } else {
+                if (COUNT) tc.tris++;
+                float t;
+                bool hit;
+                if (EXT && (tv.flags & PBRS_TRI_CHECK_SHADING)) hit = mesh_tri_shade_t(sc, s, tv, ray, t, dg);
+                else hit = mesh_tri_hit_t(tv, ray, t, dg);
+                if (hit && t < bt) { bt = t; btri = s; }
+            }
+            if (tv.flags & PBRS_TRI_LAST_IN_LEAF) return false;
+            ++s;
+        }
+    }
+
     // ---- phase 2a: a leaf ----
     PB_DEV void leaf(const DeviceScene &sc, Diag &dg, TravCount &tc) {
         const uint32_t first = next & PBRS_LEAF_FIRST_MASK;
@@ -372,31 +402,7 @@ struct Walk {
         if (in_mesh()) {
             // a run of triangles (shape/src/blas.rs:447-454): all see the extent of the pop
             Ray ray; ray.o = o; ray.d = d; ray.t_max = t_max;
-            uint32_t s = tri_base + first;
-            while (true) {
-                TriVerts tv = load_tri<true>(sc.tris + s);
-                if (EXT && (tv.flags & PBRS_TRI_SPHERE)) {
-                    // IsoBlas<Sphere>: the leaf closure is the sphere's own test (blas.rs:267-274)
-                    if (COUNT) tc.spheres++;
-                    float t;
-                    if (ball_test(tv.p0, tv.p1.x, ray, ANY, t, dg)) {
-                        if (ANY) { occluded = true; next = PBRS_DONE; return; }
-                        if (t < l_best_t) { l_best_t = t; l_best_tri = s; }
-                    }
-                } else if (ANY) {
-                    if (COUNT) tc.tris++;
-                    if (mesh_tri_occludes(tv, ray, dg)) { occluded = true; next = PBRS_DONE; return; }
-                } else {
-                    if (COUNT) tc.tris++;
-                    float t;
-                    bool hit;
-                    if (EXT && (tv.flags & PBRS_TRI_CHECK_SHADING)) hit = mesh_tri_shade_t(sc, s, tv, ray, t, dg);
-                    else hit = mesh_tri_hit_t(tv, ray, t, dg);
-                    if (hit && t < l_best_t) { l_best_t = t; l_best_tri = s; }
-                }
-                if (tv.flags & PBRS_TRI_LAST_IN_LEAF) break;
-                ++s;
-            }
+            if (run_tris(sc, tri_base + first, ray, l_best_t, l_best_tri, dg, tc)) { occluded = true; next = PBRS_DONE; return; }
             if (!ANY) t_max = l_best_t;  // blas.rs:468
             return;
         }
@@ -435,6 +441,24 @@ struct Walk {
         }
         // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
         const MeshHead mesh = load_mesh_head(sc.meshes + index);
+        if (EXT && mesh.root_is_leaf) {
+            // A mesh whose whole BLAS is one leaf (a Cornell wall: two triangles) is tested where the lane
+            // stands, in object space, without the mesh protocol (parking the world ray, reciprocal
+            // direction, EXIT entry, two phase changes for a handful of triangles).  Same decisions: the
+            // root box and every triangle see the incoming extent (blas.rs:428,441-454), the best of the
+            // run is the instance's hit (instance.rs:50-72).  Scenes with such meshes run the EXT kernels.
+            if (!box_exact(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], obj.o, obj.d, obj.t_max).pass) {
+                if (!ANY) ret = PB_INF;
+                return;
+            }
+            float bt = PB_INF;
+            uint32_t btri = PBRS_NONE;
+            if (run_tris(sc, mesh.tri_base, obj, bt, btri, dg, tc)) { occluded = true; next = PBRS_DONE; return; }
+            if (ANY) return;
+            ret = bt;
+            if (bt < PB_INF && bt <= best.t) { best.t = bt; best.inst = first; best.tri = btri; }
+            return;
+        }
         cur_inst = first;
         save_world();
         set_space(obj.o, obj.d, obj.t_max, 16u);

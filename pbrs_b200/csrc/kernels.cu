@@ -634,23 +634,30 @@ template <int INTEGRATOR>
 void launch_shade(const Grid &g, cudaStream_t stream, const DeviceScene &sc, const PathBuffers &pb, const FrameParams &fp, const BatchParams &bp,
                   uint32_t *cnt, uint32_t *next_queue, uint32_t *next_cnt, int stage) {
     const int *gs = g.shade[INTEGRATOR];
+    // (a class no instance's material belongs to has an empty queue in every stage: its kernels are not launched at all)
+    const auto has = [&sc](int cls) { return (sc.cls_mask >> cls) & 1u; };
     k_shade<PBRS_CLS_MISS, INTEGRATOR><<<gs[PBRS_CLS_MISS], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-    k_shade<PBRS_CLS_EMISSIVE, INTEGRATOR><<<gs[PBRS_CLS_EMISSIVE], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    if (has(PBRS_CLS_EMISSIVE)) k_shade<PBRS_CLS_EMISSIVE, INTEGRATOR><<<gs[PBRS_CLS_EMISSIVE], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
     if (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH && sc.shade_split) {
-        k_surface<<<g.surface, kThreads, 0, stream>>>(sc, pb, cnt, stage);
-        k_scatter<PBRS_CLS_LAMBERT><<<g.scatter[0], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-        k_scatter<PBRS_CLS_MICROFACET><<<g.scatter[1], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-        k_scatter<PBRS_CLS_MULTI><<<g.scatter[2], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        if (has(PBRS_CLS_LAMBERT) || has(PBRS_CLS_MICROFACET) || has(PBRS_CLS_MULTI)) k_surface<<<g.surface, kThreads, 0, stream>>>(sc, pb, cnt, stage);
+        if (has(PBRS_CLS_LAMBERT)) k_scatter<PBRS_CLS_LAMBERT><<<g.scatter[0], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        if (has(PBRS_CLS_MICROFACET)) k_scatter<PBRS_CLS_MICROFACET><<<g.scatter[1], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        if (has(PBRS_CLS_MULTI)) k_scatter<PBRS_CLS_MULTI><<<g.scatter[2], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
     } else {
-        k_shade<PBRS_CLS_LAMBERT, INTEGRATOR><<<gs[PBRS_CLS_LAMBERT], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-        k_shade<PBRS_CLS_MICROFACET, INTEGRATOR><<<gs[PBRS_CLS_MICROFACET], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
-        k_shade<PBRS_CLS_MULTI, INTEGRATOR><<<gs[PBRS_CLS_MULTI], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        if (has(PBRS_CLS_LAMBERT)) k_shade<PBRS_CLS_LAMBERT, INTEGRATOR><<<gs[PBRS_CLS_LAMBERT], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        if (has(PBRS_CLS_MICROFACET)) k_shade<PBRS_CLS_MICROFACET, INTEGRATOR><<<gs[PBRS_CLS_MICROFACET], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+        if (has(PBRS_CLS_MULTI)) k_shade<PBRS_CLS_MULTI, INTEGRATOR><<<gs[PBRS_CLS_MULTI], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
     }
-    k_shade<PBRS_CLS_SPECULAR, INTEGRATOR><<<gs[PBRS_CLS_SPECULAR], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
+    if (has(PBRS_CLS_SPECULAR)) k_shade<PBRS_CLS_SPECULAR, INTEGRATOR><<<gs[PBRS_CLS_SPECULAR], kThreads, 0, stream>>>(sc, pb, fp, bp, cnt, next_queue, next_cnt, stage);
 }
 // kernels launched by launch_shade
 template <int INTEGRATOR>
-int shade_launches(const DeviceScene &sc) { return (PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH && sc.shade_split) ? PBRS_NUM_CLS + 1 : PBRS_NUM_CLS; }
+int shade_launches(const DeviceScene &sc) {
+    const auto has = [&sc](int cls) { return (int)((sc.cls_mask >> cls) & 1u); };
+    const int heavy = has(PBRS_CLS_LAMBERT) + has(PBRS_CLS_MICROFACET) + has(PBRS_CLS_MULTI);
+    const bool split = PBRS_SHADE_SPLIT && INTEGRATOR == PBRS_INTEGRATOR_PATH && sc.shade_split;
+    return 1 + has(PBRS_CLS_EMISSIVE) + has(PBRS_CLS_SPECULAR) + heavy + (split && heavy ? 1 : 0);
+}
 template <int INTEGRATOR>
 void size_shade(Grid &g, int sms);
 

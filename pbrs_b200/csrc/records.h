@@ -241,6 +241,7 @@ struct DeviceScene {
     uint32_t shade_split;  // the path integrator shades the heavy classes with k_surface + k_scatter (scenes of big meshes)
     uint32_t coop_closest; // closest-hit walks test their leaf runs cooperatively (scenes with >= 1024 triangles)
     uint32_t has_ext;  // any quad / cuboid / disk instance or sphere BLAS: selects the EXT traversal kernels
+    uint32_t cls_mask; // bit c: some instance's material is of shade class c (the miss class always is): absent classes' kernels are not launched
 };
 
 }  // namespace pbrs

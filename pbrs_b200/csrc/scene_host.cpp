@@ -695,9 +695,11 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     if (const char *e = std::getenv("PBRS_COOP_CLOSEST")) ds.coop_closest = (uint32_t)std::atoi(e);  // development knob
     ds.shade_split = f.tris.size() >= 100000 ? 1u : 0u;  // shade -11 % on the 1 M-triangle terrain, +12..18 % on sphere / small-mesh scenes
     if (const char *e = std::getenv("PBRS_SHADE_SPLIT")) ds.shade_split = (uint32_t)std::atoi(e);
+    ds.cls_mask = 1u << PBRS_CLS_MISS;
+    for (const InstShadeRec &r : f.shade) ds.cls_mask |= 1u << r.cls;
     ds.has_ext = s.simples.empty() ? 0u : 1u;
     for (const HostMesh &m : s.meshes)
-        if (!m.balls.empty()) ds.has_ext = 1u;
+        if (!m.balls.empty() || m.root_is_leaf) ds.has_ext = 1u;  // (one-leaf meshes are tested in place by the EXT kernels: device_walk.cuh)
     for (const TriRec &t : f.tris)
         if (t.flags & PBRS_TRI_CHECK_SHADING) { ds.has_ext = 1u; break; }
 }

@@ -32,6 +32,7 @@ WANT = {
     "l2_hit_pct": "lts__t_sector_hit_rate.pct",
     "dram_pct_of_peak": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "registers": "launch__registers_per_thread",
+    "l1_pipe_pct": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
 }
 acc = {}
 for r in rows[2:]:
@@ -55,7 +56,7 @@ for kind, recs in acc.items():
         vals = [x[key] for x in recs if key in x]
         if not vals:
             continue
-        if key in ("lanes_per_inst", "occupancy_pct", "issue_active_pct", "l1_hit_pct", "l2_hit_pct", "dram_pct_of_peak"):
+        if key in ("lanes_per_inst", "occupancy_pct", "issue_active_pct", "l1_hit_pct", "l2_hit_pct", "dram_pct_of_peak", "l1_pipe_pct"):
             w = [x.get("ms", 1.0) for x in recs if key in x]  # time-weighted
             m[key] = sum(v * t for v, t in zip(vals, w)) / max(sum(w), 1e-30)
         elif key == "registers":

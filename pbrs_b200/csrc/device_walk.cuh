@@ -441,24 +441,9 @@ struct Walk {
         }
         // a mesh: its root box sees the incoming extent (blas.rs:428 and the root's own pop, :441)
         const MeshHead mesh = load_mesh_head(sc.meshes + index);
-        if (EXT && mesh.root_is_leaf) {
-            // A mesh whose whole BLAS is one leaf (a Cornell wall: two triangles) is tested where the lane
-            // stands, in object space, without the mesh protocol (parking the world ray, reciprocal
-            // direction, EXIT entry, two phase changes for a handful of triangles).  Same decisions: the
-            // root box and every triangle see the incoming extent (blas.rs:428,441-454), the best of the
-            // run is the instance's hit (instance.rs:50-72).  Scenes with such meshes run the EXT kernels.
-            if (!box_exact(mesh.bmin[0], mesh.bmin[1], mesh.bmin[2], mesh.bmax[0], mesh.bmax[1], mesh.bmax[2], obj.o, obj.d, obj.t_max).pass) {
-                if (!ANY) ret = PB_INF;
-                return;
-            }
-            float bt = PB_INF;
-            uint32_t btri = PBRS_NONE;
-            if (run_tris(sc, mesh.tri_base, obj, bt, btri, dg, tc)) { occluded = true; next = PBRS_DONE; return; }
-            if (ANY) return;
-            ret = bt;
-            if (bt < PB_INF && bt <= best.t) { best.t = bt; best.inst = first; best.tri = btri; }
-            return;
-        }
+        // (Testing a one-leaf mesh -- a Cornell wall: two triangles -- in place, without the mesh protocol,
+        // was measured: the exact root-box test it needs and the EXT kernels it selects cost more than the
+        // protocol saves; C1 extend +6 %, C5 +9 %: profiles/r2_exp_inplace_leaf_mesh_class_mask.log)
         cur_inst = first;
         save_world();
         set_space(obj.o, obj.d, obj.t_max, 16u);

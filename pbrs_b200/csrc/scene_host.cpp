@@ -699,7 +699,7 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     for (const InstShadeRec &r : f.shade) ds.cls_mask |= 1u << r.cls;
     ds.has_ext = s.simples.empty() ? 0u : 1u;
     for (const HostMesh &m : s.meshes)
-        if (!m.balls.empty() || m.root_is_leaf) ds.has_ext = 1u;  // (one-leaf meshes are tested in place by the EXT kernels: device_walk.cuh)
+        if (!m.balls.empty()) ds.has_ext = 1u;
     for (const TriRec &t : f.tris)
         if (t.flags & PBRS_TRI_CHECK_SHADING) { ds.has_ext = 1u; break; }
 }

@@ -325,7 +325,7 @@ def main():
         achieved = ext_b / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         ev = ncu_evidence(args.workload) if args.frame_scale == 1.0 else {}
         limiter = "not profiled for this workload"
-        if ev:
+        if ev.get("lanes_per_inst"):
             limiter = (f"the SM's L1 load pipe, issue slots and SIMT efficiency, not DRAM (ncu: L1 data-pipe wavefronts {ev.get('l1_pipe_pct', 0):.0f} % of peak, DRAM at "
                        f"{ev.get('dram_pct_of_peak', 0):.1f} % of peak, issue slots {ev.get('issue_active_pct', 0):.0f} % busy, "
                        f"{ev.get('lanes_per_inst', 0):.1f} of 32 lanes per instruction, {ev.get('occupancy_pct', 0):.0f} % occupancy)")

@@ -81,11 +81,29 @@ __device__ __forceinline__ void flush_count(unsigned long long *stats, const Tra
         if (uint32_t idx = _b + lane_id(); true)                                                      \
             if (bool active = idx < _n; true)
 
+// A warp takes 128 consecutive paths per round and appends their live ones with ONE atomicAdd: the
+// queue counter is a single address, on which the L2 serialises every atomic (about half of this
+// kernel's time with one atomic per 32 paths; the queue's order is irrelevant to the film).
 __global__ void __launch_bounds__(kThreads) k_generate(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *out_count) {
-    PBRS_WARP_LOOP(bp.n_paths, j, active) {
-        bool live = active && stage_generate(sc, pb, fp, bp, j);
-        uint32_t slot = warp_push(out_count, live);
-        if (live) pb.queue[0][slot] = j;
+    const uint32_t n = bp.n_paths, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 128u; b < n; b += warps * 128u) {
+        unsigned m[4];
+        uint32_t total = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t j = b + 32u * k + lane_id();
+            m[k] = __ballot_sync(0xFFFFFFFFu, j < n && stage_generate(sc, pb, fp, bp, j));
+            total += (uint32_t)__popc(m[k]);
+        }
+        if (total == 0u) continue;
+        uint32_t base = 0u;
+        if (lane_id() == 0u) base = atomicAdd(out_count, total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((m[k] >> lane_id()) & 1u) pb.queue[0][base + (uint32_t)__popc(m[k] & ((1u << lane_id()) - 1u))] = b + 32u * k + lane_id();
+            base += (uint32_t)__popc(m[k]);
+        }
     }
 }
 

@@ -22,9 +22,30 @@
 #include <cuda_runtime.h>
 #define PB_DEV __host__ __device__ __forceinline__
 #define PB_CALL __host__ __device__ __noinline__
+// Functions whose struct arguments (Isect, AreaLight, out-parameters) live in local memory for the
+// duration of an out-of-line call: inlined (0 = keep them out of line).  Measured: shade -8 % on C4,
+// -13 % on C5, -18 % on C1 for the price of ~10 % more SASS (profiles/r2_exp_shade_inline_gridconstant.log).
+#ifndef PBRS_INLINE_RECON
+#define PBRS_INLINE_RECON 1
+#endif
+#ifndef PBRS_INLINE_AREA
+#define PBRS_INLINE_AREA 1
+#endif
+#if PBRS_INLINE_RECON
+#define PB_CALL_RECON PB_DEV
+#else
+#define PB_CALL_RECON PB_CALL
+#endif
+#if PBRS_INLINE_AREA
+#define PB_CALL_AREA PB_DEV
+#else
+#define PB_CALL_AREA PB_CALL
+#endif
 #else
 #define PB_DEV inline
 #define PB_CALL inline
+#define PB_CALL_RECON inline
+#define PB_CALL_AREA inline
 #endif
 
 namespace pbrs {
@@ -94,6 +115,9 @@ PB_DEV float t_hypot(float x, float y) { return (float)sqrt((double)x * (double)
 struct Diag {
     uint32_t panics;
 };
+// (Keeping the bits in a shared-memory word per thread instead of the object -- which out-of-line
+// callees pin to local memory -- was measured: no gain in the shade kernels, +1.5 % in the traversal
+// kernels; profiles/r2_exp_shade_inline_gridconstant.log)
 PB_DEV void flag(Diag &d, int kind) { d.panics |= 1u << kind; }
 enum {
     P_SPHERE_INSIDE = 0, P_TBN = 1, P_HAT = 2, P_BSDF_FRAME = 3, P_MESH_UV = 4, P_EMPTY_BXDFS = 5,

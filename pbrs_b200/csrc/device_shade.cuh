@@ -365,24 +365,33 @@ template <int CLS>
 PB_DEV void bxdfs_at_t(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
     L.n = 0;
     color ca = mkc(m.a[0], m.a[1], m.a[2]), cb = mkc(m.b[0], m.b[1], m.b[2]);
+    // A class whose lobes are all of one kind (Lambert, microfacet, specular) has materials of at most
+    // ONE lobe: it goes to slot 0 with a static index, and the BSDF routines below read slot 0 only, so
+    // the lobe stays in registers (a dynamically indexed Lobes lives in local memory: the Lambert scatter
+    // kernel read its albedo back from there ~25 times per path).
+    constexpr bool single = cls_lobe_kind(CLS) >= 0;
+    auto put = [&L](const Lobe &l) {
+        if constexpr (single) { L.l[0] = l; L.n = 1; }
+        else L.l[L.n++] = l;
+    };
     if (cls_has(CLS, PBRS_MTL_LAMBERTIAN) && m.kind == PBRS_MTL_LAMBERTIAN) {  // :180-184
-        L.l[L.n++] = mk_lambert(texture_value(sc, m.tex_kd, h.u, h.v, h.pos, dg));
+        put(mk_lambert(texture_value(sc, m.tex_kd, h.u, h.v, h.pos, dg)));
     }
     if (cls_has(CLS, PBRS_MTL_METAL) && m.kind == PBRS_MTL_METAL) {  // :200-206
         float alpha = roughness_to_alpha(m.f[0]);
         Lobe l = mk_microfacet(grayc(1.0f), alpha, alpha);
         l.fresnel = FR_CONDUCTOR; l.eta_t = ca; l.k = cb;
-        L.l[L.n++] = l;
+        put(l);
     }
     if (cls_has(CLS, PBRS_MTL_GLOSSY) && m.kind == PBRS_MTL_GLOSSY) {  // :72-78, :216-218
         float alpha = roughness_to_alpha(m.f[0]);
-        L.l[L.n++] = mk_microfacet(ca, alpha, alpha);
+        put(mk_microfacet(ca, alpha, alpha));
     }
     if (cls_has(CLS, PBRS_MTL_MIRROR) && m.kind == PBRS_MTL_MIRROR) {  // :229-232
-        L.l[L.n++] = mk_specular(ca, INTR_REFLECTION, FR_NOP, 0.0f, 0.0f);
+        put(mk_specular(ca, INTR_REFLECTION, FR_NOP, 0.0f, 0.0f));
     }
     if (cls_has(CLS, PBRS_MTL_DIELECTRIC) && m.kind == PBRS_MTL_DIELECTRIC) {  // :265-268
-        L.l[L.n++] = mk_specular(ca, INTR_HYBRID, FR_DIELECTRIC, 1.0f, m.f[0]);
+        put(mk_specular(ca, INTR_HYBRID, FR_DIELECTRIC, 1.0f, m.f[0]));
     }
     // DiffuseLight (:291-293): no lobes
     if (cls_has(CLS, PBRS_MTL_PLASTIC) && m.kind == PBRS_MTL_PLASTIC) {  // :433-445
@@ -414,7 +423,7 @@ PB_DEV void bxdfs_at_t(const DeviceScene &sc, const MaterialRec &m, const Isect 
     }
     if (cls_has(CLS, PBRS_MTL_SUBSTRATE) && m.kind == PBRS_MTL_SUBSTRATE) {  // :393-420 (FresnelBlend is commented out upstream: Lambert only)
         color d = texture_value(sc, m.tex_kd, h.u, h.v, h.pos, dg), s = texture_value(sc, m.tex_ks, h.u, h.v, h.pos, dg);
-        if (!(is_black(d) && is_black(s))) L.l[L.n++] = mk_lambert(d);
+        if (!(is_black(d) && is_black(s))) put(mk_lambert(d));
     }
 }
 
@@ -448,7 +457,8 @@ PB_DEV color bsdf_eval_t(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, 
     vec3 wo = to_local(fr, wo_w, dg);
     if (wo.z == 0.0f) return blackc();
     color s = blackc();
-    for (int i = 0; i < L.n; ++i) s = s + lobe_eval<K>(L.l[i], wo, wi, dg);
+    if constexpr (K >= 0) { if (L.n > 0) s = s + lobe_eval<K>(L.l[0], wo, wi, dg); }  // single-lobe class: slot 0, static index
+    else for (int i = 0; i < L.n; ++i) s = s + lobe_eval<K>(L.l[i], wo, wi, dg);
     return s;
 }
 template <int K>
@@ -456,9 +466,16 @@ PB_DEV float bsdf_pdf_t(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, D
     vec3 wi = to_local(fr, wi_w, dg);
     vec3 wo = to_local(fr, wo_w, dg);
     float s = 0.0f;
-    for (int i = 0; i < L.n; ++i) {
-        Prob p = lobe_prob<K>(L.l[i], wo, wi, dg);
-        s += p.is_mass ? 0.0f : p.v;
+    if constexpr (K >= 0) {
+        if (L.n > 0) {
+            Prob p = lobe_prob<K>(L.l[0], wo, wi, dg);
+            s += p.is_mass ? 0.0f : p.v;
+        }
+    } else {
+        for (int i = 0; i < L.n; ++i) {
+            Prob p = lobe_prob<K>(L.l[i], wo, wi, dg);
+            s += p.is_mass ? 0.0f : p.v;
+        }
     }
     return s;
 }
@@ -471,9 +488,11 @@ PB_DEV void bsdf_sample_t(const Frame &fr, const Lobes &L, vec3 wo_world, float 
     vec3 wo = to_local(fr, wo_world, dg);
     int n = L.n;
     if (n == 0) { f = blackc(); wi_out = mk(0.0f, 0.0f, 0.0f); pr = Mass(0.0f); return; }
+    if constexpr (K >= 0) n = 1;  // single-lobe class
     float un = u * (float)n;
     int chosen = (int)un;
     if (chosen >= n) chosen = n - 1;
+    if constexpr (K >= 0) chosen = 0;  // (what the two lines above give for n = 1: a static index)
     float remapped_u = fractf(un);
     color value;
     vec3 wi;
@@ -524,14 +543,24 @@ template <int K>
 PB_DEV bool bsdf_sample_specular(const Frame &fr, const Lobes &L, vec3 wo_world, color &f, vec3 &wi_out, Prob &pr, Diag &dg) {
     if constexpr (K >= 0 && K != LOBE_SPECULAR) return false;
     vec3 wo = to_local(fr, wo_world, dg);
-    for (int i = 0; i < L.n; ++i)
-        if (kind_of<K>(L.l[i]) == LOBE_SPECULAR) {
+    if constexpr (K >= 0) {  // the specular class: one lobe, slot 0
+        if (L.n > 0) {
             vec3 wi;
-            lobe_sample<K>(L.l[i], wo, 0.0f, 0.0f, f, wi, pr, dg);
+            lobe_sample<K>(L.l[0], wo, 0.0f, 0.0f, f, wi, pr, dg);
             wi_out = to_world(fr, wi);
             return true;
         }
-    return false;
+        return false;
+    } else {
+        for (int i = 0; i < L.n; ++i)
+            if (kind_of<K>(L.l[i]) == LOBE_SPECULAR) {
+                vec3 wi;
+                lobe_sample<K>(L.l[i], wo, 0.0f, 0.0f, f, wi, pr, dg);
+                wi_out = to_world(fr, wi);
+                return true;
+            }
+        return false;
+    }
 }
 
 // ---- environment: scene/src/lib.rs:96-117; scene/src/preset.rs:25-51 ----
@@ -576,7 +605,7 @@ PB_DEV void sphere_sample(vec3 c, float radius, float u, float v, vec3 &pos, vec
     normal = dir;
 }
 // :197-236
-PB_CALL void sphere_sample_towards(vec3 c, float radius, vec3 target, float u, float v, vec3 &pos, vec3 &normal, Diag &dg) {
+PB_CALL_AREA void sphere_sample_towards(vec3 c, float radius, vec3 target, float u, float v, vec3 &pos, vec3 &normal, Diag &dg) {
     vec3 wc = c - target;
     float r2 = radius * radius;
     if (len2(wc) < r2) { sphere_sample(c, radius, u, v, pos, normal); return; }
@@ -636,7 +665,7 @@ PB_DEV AreaLight load_area_light(const AreaLightRec *r) {
     l.area = r->area;
     return l;
 }
-PB_CALL bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, vec3 &normal, Diag &dg) {
+PB_CALL_AREA bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, vec3 &normal, Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) {
         Isect h;
         if (!sphere_intersect(l.p0, l.p1.x, r, h, dg, false)) return false;
@@ -654,7 +683,7 @@ PB_CALL bool area_shape_intersect(const AreaLight &l, const Ray &r, vec3 &pos, v
     return true;
 }
 // sample_shape.rs:28-33 default pdf_at (Q12: distance, not distance squared); sphere override :238
-PB_CALL bool area_shape_pdf_at(const AreaLight &l, const Isect &ref, vec3 wi, float &pdf, Diag &dg) {
+PB_CALL_AREA bool area_shape_pdf_at(const AreaLight &l, const Isect &ref, vec3 wi, float &pdf, Diag &dg) {
     if (l.kind == PBRS_AREA_SPHERE) return sphere_pdf_at(l.p0, l.p1.x, ref.pos, wi, pdf);
     Ray ray = spawn_ray(ref, wi);
     vec3 pos, normal;

@@ -192,7 +192,7 @@ PB_DEV void stage_extend(const DeviceScene &sc, const PathBuffers &pb, uint32_t 
 // = ray to object space, the shape's own intersect for the winning primitive, hit back to world
 // (geometry/src/transform.rs:309-320).  Same inputs, same operations as during the walk, so the
 // values equal what the reference computed when it found the hit.
-PB_CALL void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32_t inst, uint32_t tri, Isect &out, uint32_t &material,
+PB_CALL_RECON void reconstruct_hit(const DeviceScene &sc, const Ray &world_ray, uint32_t inst, uint32_t tri, Isect &out, uint32_t &material,
                             Diag &dg) {
     Ray wr = world_ray;
     wr.t_max = PB_INF;

@@ -22,6 +22,18 @@ namespace pbrs {
 namespace {
 
 constexpr int kThreads = 128;
+// Kernel parameters that are handed on by reference to out-of-line device functions (the scene, the
+// path buffers): __grid_constant__ lets their address be taken in place, in the constant bank; without
+// it every such kernel starts by copying the struct into its local-memory stack frame and the callees
+// read the scene through local loads.
+#ifndef PBRS_GRID_CONSTANT
+#define PBRS_GRID_CONSTANT 1
+#endif
+#if PBRS_GRID_CONSTANT
+#define PBRS_GC const __grid_constant__
+#else
+#define PBRS_GC
+#endif
 #ifndef PBRS_LANES
 #define PBRS_LANES 2
 #endif
@@ -247,7 +259,7 @@ struct SmemStack {
 };
 
 template <bool ANY, bool COUNT, bool EXT>
-__global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
+__global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(PBRS_GC DeviceScene sc, PBRS_GC PathBuffers pb, const uint32_t *queue, uint32_t *cnt) {
     const uint32_t *count = cnt + (ANY ? PBRS_CNT_SHADOW : PBRS_CNT_EXTEND);
     uint32_t *cursor = cnt + (ANY ? PBRS_CNT_SHADOW_CURSOR : PBRS_CNT_EXTEND_CURSOR);
     Diag dg; dg.panics = 0u;
@@ -541,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(De
 #define PBRS_SCATTER_BLOCKS_PER_SM 4
 #endif
 template <int CLS, int INTEGRATOR>
-__global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
+__global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(PBRS_GC DeviceScene sc, PBRS_GC PathBuffers pb, PBRS_GC FrameParams fp, PBRS_GC BatchParams bp, uint32_t *cnt,
                                                     uint32_t *next_queue, uint32_t *next_cnt, int bounce) {
     Diag dg; dg.panics = 0u;
     uint32_t rays = 0u;
@@ -566,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_SHADE_BLOCKS_PER_SM) k_shade(De
     flush_diag(pb.stats, dg);
 }
 // the three heavy classes' queues, one after the other
-__global__ void __launch_bounds__(kThreads, PBRS_SURFACE_BLOCKS_PER_SM) k_surface(DeviceScene sc, PathBuffers pb, const uint32_t *cnt, int bounce) {
+__global__ void __launch_bounds__(kThreads, PBRS_SURFACE_BLOCKS_PER_SM) k_surface(PBRS_GC DeviceScene sc, PBRS_GC PathBuffers pb, const uint32_t *cnt, int bounce) {
     Diag dg; dg.panics = 0u;
     const int classes[3] = {PBRS_CLS_LAMBERT, PBRS_CLS_MICROFACET, PBRS_CLS_MULTI};
 #pragma unroll 1
@@ -580,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_SURFACE_BLOCKS_PER_SM) k_surfac
     flush_diag(pb.stats, dg);
 }
 template <int CLS>
-__global__ void __launch_bounds__(kThreads, PBRS_SCATTER_BLOCKS_PER_SM) k_scatter(DeviceScene sc, PathBuffers pb, FrameParams fp, BatchParams bp, uint32_t *cnt,
+__global__ void __launch_bounds__(kThreads, PBRS_SCATTER_BLOCKS_PER_SM) k_scatter(PBRS_GC DeviceScene sc, PBRS_GC PathBuffers pb, PBRS_GC FrameParams fp, PBRS_GC BatchParams bp, uint32_t *cnt,
                                                                                   uint32_t *next_queue, uint32_t *next_cnt, int bounce) {
     Diag dg; dg.panics = 0u;
     uint32_t rays = 0u;

@@ -693,7 +693,12 @@ void fill_scene_constants(const SceneImpl &s, const FlatScene &f, DeviceScene &d
     ds.has_mesh = s.meshes.empty() ? 0u : 1u;
     ds.coop_closest = f.tris.size() >= 1024 ? 1u : 0u;  // a Cornell box (34 triangles) loses 8 % of its extend time to the bookkeeping
     if (const char *e = std::getenv("PBRS_COOP_CLOSEST")) ds.coop_closest = (uint32_t)std::atoi(e);  // development knob
-    ds.shade_split = f.tris.size() >= 100000 ? 1u : 0u;  // shade -11 % on the 1 M-triangle terrain, +12..18 % on sphere / small-mesh scenes
+    // The split shade kernels (k_surface + k_scatter) were a gain on big meshes (-11 % on the 1 M-triangle
+    // terrain) only while the one-piece kernels kept their Interaction, lobes and scene in local memory;
+    // since those live in registers / the constant bank the one-piece kernels win everywhere (C4 shade
+    // -13 %, C5 -23 %, C3 -20 % against the split: profiles/r2_exp_shade_inline_gridconstant.log), so the
+    // split is off unless asked for.
+    ds.shade_split = 0u;
     if (const char *e = std::getenv("PBRS_SHADE_SPLIT")) ds.shade_split = (uint32_t)std::atoi(e);
     ds.cls_mask = 1u << PBRS_CLS_MISS;
     for (const InstShadeRec &r : f.shade) ds.cls_mask |= 1u << r.cls;

@@ -264,8 +264,10 @@ int pbrs_render_device(const pbrs_scene *, const pbrs_render_opts *, float *d_fi
 
 /* After the caller has synchronised the stream a pbrs_render_device frame was enqueued on: fails
  * (PBRS_ERR_UNSUPPORTED) if a traversal stack overflowed during that frame.  pbrs_render,
- * pbrs_render_ids and pbrs_render_samples check this themselves.  (pbrs_scene_commit rejects every
- * scene whose BVH depths could overflow the stack, so this is defence in depth.) */
+ * pbrs_render_ids and pbrs_render_samples check this themselves.  pbrs_scene_commit rejects every
+ * scene whose BVH depths could overflow the stack, so this is defence in depth: the overflow test
+ * itself runs in frames rendered with PBRS_FLAG_COUNT_TRAVERSAL (the counting kernels); the plain
+ * kernels rely on the commit-time bound. */
 int pbrs_check_last_frame(const pbrs_scene *);
 
 /* Page-locked host memory for the film: the DMA target of pbrs_render's device-to-host copies

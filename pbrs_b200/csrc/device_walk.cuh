@@ -163,7 +163,7 @@ struct alignas(8) StackPair {
     uint32_t ref;
     float tl;
 };
-template <bool ANY>
+template <bool ANY, bool CHECK = true>
 struct ArrayStack {
     using Entry = typename std::conditional<ANY, uint32_t, StackPair>::type;
     Entry *ent;
@@ -172,8 +172,13 @@ struct ArrayStack {
     PB_DEV ArrayStack(Entry *e, uint32_t *p) : ent(e), park(p), sp(0) {}
     PB_DEV void reset() { sp = 0; }
     PB_DEV bool empty() const { return sp == 0; }
+    // CHECK = false: no overflow test.  pbrs_scene_commit bounds TLAS depth + BLAS depth + 2 by the stack
+    // size (scene_host.cpp) and at most one entry per level plus the EXIT tag is alive at once, so the
+    // test can never fire on a committed scene; it costs 1-3 % of the traversal kernels
+    // (profiles/r2_exp_stack_check_votes.log).  The counting kernels, which the parity tests run on every
+    // scene, and the host build keep it.
     PB_DEV void push(uint32_t r, float t, Diag &dg) {
-        if (sp < PBRS_WALK_STACK) {
+        if (!CHECK || sp < PBRS_WALK_STACK) {
             if constexpr (ANY) ent[sp] = r;
             else { StackPair e; e.ref = r; e.tl = t; ent[sp] = e; }
             ++sp;

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, PBRS_TRACE_BLOCKS_PER_SM) k_trace(PB
     __shared__ typename Stk::Entry ring_mem[Stk::S * kThreads];
     Walk<ANY, COUNT, EXT, Stk> w(Stk(ring_mem + threadIdx.x, st_ref, st_tl));
 #else
-    using Stk = ArrayStack<ANY>;
+    using Stk = ArrayStack<ANY, COUNT>;
     alignas(16) typename Stk::Entry st_mem[PBRS_WALK_STACK + PBRS_WALK_PARK];  // (closest-hit: the park words take half of their 16 entries)
     Walk<ANY, COUNT, EXT, Stk> w(Stk(st_mem, reinterpret_cast<uint32_t *>(st_mem + PBRS_WALK_STACK)));
 #endif

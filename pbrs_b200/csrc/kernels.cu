@@ -35,8 +35,10 @@ constexpr int kThreads = 128;
 #define PBRS_GC
 #endif
 #ifndef PBRS_LANES
-#define PBRS_LANES 2
+#define PBRS_LANES 3  // batches in flight on their own streams: 3 beats 2 by 1.0 % on the full C4 frame, 4 equals 3 (profiles/r2_exp_lanes.log)
 #endif
+constexpr int kMaxLanes = 4;
+static_assert(PBRS_LANES >= 1 && PBRS_LANES <= kMaxLanes, "PBRS_LANES");
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
@@ -721,15 +723,15 @@ void size_shade(Grid &g, int sms) {
 
 struct Workspace {
     int device = -1;
-    // Two lanes: consecutive batches alternate between two sets of path buffers on two streams, so
-    // that the tail of one batch's persistent kernels (a few straggling warps) overlaps the next
-    // batch's work instead of leaving SMs idle.
+    // Lanes: consecutive batches rotate over PBRS_LANES sets of path buffers, each on its own stream, so
+    // that the tail of one batch's persistent kernels (a few straggling warps) and its small late-bounce
+    // kernels overlap the other batches' work instead of leaving SMs idle.
     uint32_t capacity = 0;
     int n_lanes = 0;
-    char *slab[2] = {nullptr, nullptr};
-    PathBuffers pb[2]{};
-    cudaStream_t lane_stream[2] = {nullptr, nullptr};
-    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
+    char *slab[kMaxLanes] = {};
+    PathBuffers pb[kMaxLanes]{};
+    cudaStream_t lane_stream[kMaxLanes] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[kMaxLanes] = {};
     uint32_t *counts = nullptr;
     uint32_t counts_cap = 0;   // in batches
     uint32_t *tiles = nullptr;
@@ -793,7 +795,7 @@ static int workspace_prepare(Workspace *&wp, int device, uint32_t capacity, int 
     if (!w.ev[0]) { CK(cudaEventCreate(&w.ev[0])); CK(cudaEventCreate(&w.ev[1])); }
     if (!w.stats) CK(cudaMalloc(&w.stats, sizeof(unsigned long long) * kStatCount));
     if (!w.lane_stream[0]) {
-        for (int l = 0; l < 2; ++l) { CK(cudaStreamCreateWithFlags(&w.lane_stream[l], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.join_ev[l], cudaEventDisableTiming)); }
+        for (int l = 0; l < kMaxLanes; ++l) { CK(cudaStreamCreateWithFlags(&w.lane_stream[l], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&w.join_ev[l], cudaEventDisableTiming)); }
         CK(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&w.graph_stream, cudaStreamNonBlocking));
     }
@@ -1054,7 +1056,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
         fpk.flags = fp.flags; fpk.x0 = fp.x0; fpk.y0 = fp.y0; fpk.x1 = fp.x1; fpk.y1 = fp.y1; fpk.width = fp.width; fpk.height = fp.height;
         fpk.tiles = fp.tiles; fpk.n_tiles = fp.n_tiles;
         put(shape, sizeof shape); put(&fpk, sizeof fpk); put(&total_pixels, sizeof total_pixels);
-        const void *ptrs[13] = {tg.film, tg.samples, tg.ids_inst, tg.ids_prim, tg.ids_t, w.slab[0], w.slab[1], w.counts, w.stats, w.tiles,
+        const void *ptrs[15] = {tg.film, tg.samples, tg.ids_inst, tg.ids_prim, tg.ids_t, w.slab[0], w.slab[1], w.slab[2], w.slab[3], w.counts, w.stats, w.tiles,
                                 r.dscene.tlas_nodes, r.dscene.inst_trav, band_copies ? tg.host_film : nullptr};
         put(ptrs, sizeof ptrs);
         if (!w.graph_exec || key != w.graph_key) {

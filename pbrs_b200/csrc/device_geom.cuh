@@ -9,7 +9,7 @@
 //   BLAS closest  shape/src/blas.rs:422-476  (explicit stack, near child first by split axis)
 //   BLAS any      shape/src/blas.rs:478-495
 // What differs is the data layout: one 64-byte record holds BOTH children's boxes, so a node is
-// fetched once per expansion with four 16-byte loads, and the far child waits on the stack with
+// fetched once per expansion with two 32-byte loads, and the far child waits on the stack with
 // its entry distance instead of being re-fetched.
 #pragma once
 #include "../../include/pbrs_gpu.h"

@@ -918,7 +918,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
     uint32_t ppb = std::max<uint32_t>(1u, capacity / std::max(fp.spp_r, 1u));  // pixels per batch
     // End-to-end path (pbrs_render into a page-locked film, whole frame, no tile split): batches of
     // whole tile rows are contiguous row bands of the film, so each batch's band goes home on its own
-    // lane stream as soon as it is accumulated -- the copy overlaps the other lane's kernels.  A frame
+    // lane stream as soon as it is accumulated -- the copy overlaps the other lanes' kernels.  A frame
     // that would fit one batch is cut in up to four, else the copy could not overlap anything.
     tg.host_copied = false;
     bool band_copies = false;
@@ -940,7 +940,7 @@ int render_frame(const SceneImpl &s, Replica &r, const pbrs_render_opts &o, cons
 
     const bool count_trav = (o.flags & PBRS_FLAG_COUNT_TRAVERSAL) != 0;
     const bool want_stats = st != nullptr;
-    // per-stage timing needs one in-order stream; everything else pipelines batches over two lanes
+    // per-stage timing needs one in-order stream; everything else pipelines batches over PBRS_LANES lanes
     const int n_lanes = (n_batches >= 2 && !(want_stats && (o.flags & PBRS_FLAG_TIME_STAGES))) ? PBRS_LANES : 1;
     Workspace *&wp = r.workspace;
     int rc = workspace_prepare(wp, r.device, capacity, n_lanes, std::max(n_batches, 1u), std::max(fp.n_tiles, 1u));

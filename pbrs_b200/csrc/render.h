@@ -17,7 +17,7 @@ struct RenderTargets {
     float *ids_t = nullptr;
     int32_t only_sample = -1;
     // pbrs_render with a page-locked host film: the frame is cut into batches of whole tile rows and
-    // every finished batch's rows are copied out on its own lane stream while the other lane renders
+    // every finished batch's rows are copied out on its own lane stream while the other lanes render
     // (render_frame sets host_copied when it did so; otherwise the caller copies the film at the end)
     float *host_film = nullptr;
     mutable bool host_copied = false;

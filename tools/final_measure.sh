@@ -2,7 +2,7 @@
 #   1. GPU suite with PBRS_WRITE_OUTLIERS=1 (measured outlier counts), smoke()
 #   2. the default bench command + its reference arm; bench lines of the other BASELINE configs
 #   3. ncu metric pass over all bounces of two whole mid-frame batches of the full-size C4 frame -> profiles/r2_traffic.json
-#   4. ncu launch list (gpu__time_duration only) of 190 consecutive mid-frame launches of the default bench command
+#   4. ncu launch list (gpu__time_duration only) of every kernel of a quarter-size C4 frame
 #   5. ncu --set full captures -> markdown summaries (tools/ncu_md.py) of: any-hit walk of bounce 0 + closest-hit walk of bounce 1 (C4),
 #      the Lambert shade kernel of bounce 0 (C4), the closest-hit walk of bounce 1 (C5)
 cd $GRAFT_REPO_ROOT
@@ -20,9 +20,9 @@ METRICS=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t
 timeout 900 ncu --metrics $METRICS --clock-control none -k regex:k_trace -s 1920 -c 20 -f -o /tmp/r2_trace_metrics python tools/one_frame.py libpbrs_gpu.so c4 1.0 2 > $O/final_ncu_metrics.log 2>&1; tail -1 $O/final_ncu_metrics.log
 python tools/ncu_traffic.py /tmp/r2_trace_metrics.ncu-rep c4 --store 2>&1 | tail -3
 cp profiles/r2_traffic.json $O/
-# launch list of the bench command itself: 37 launches per batch, 128 batches per frame; the counter frame and three warm-up frames come
-# first (4 x 4736 launches), -s lands in the middle of the first timed frame
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 21300 -c 190 --csv --log-file $O/final_launches_c4.csv python bench.py --no-cpu --steps 1 --warmup 3 > $O/final_ncu_list.log 2>&1; tail -1 $O/final_ncu_list.log | cut -c1-200
+# launch list: every kernel of a quarter-size frame (same batch size, same launches per batch as the full frame).  NOT the full bench
+# command: ncu intercepts every launch it skips, and the 25 000 launches before the timed frame took more than 25 minutes when tried.
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/final_launch_list_c4_quarter.csv python tools/one_frame.py libpbrs_gpu.so c4 0.25 2 > $O/final_ncu_list.log 2>&1; tail -1 $O/final_ncu_list.log | cut -c1-200
 # source-level captures -> markdown
 mkdir -p /tmp/cub && (cd /tmp/cub && rm -f *.cubin *.dis && cuobjdump -xelf all $GRAFT_REPO_ROOT/pbrs_b200/lib/libpbrs_gpu.so > /dev/null && nvdisasm -g -c kernels.sm_100a.cubin > kernels.sm_100a.cubin.dis 2>/dev/null)
 RUN="python tools/one_frame.py libpbrs_gpu.so c4 0.25 2"

@@ -42,6 +42,14 @@ PB_DEV vec3 cos_sample_hemisphere(float u, float v) {
     return mk(x, y, z);
 }
 
+#ifndef PBRS_INLINE_DYN
+#define PBRS_INLINE_DYN 1  // the multi-lobe class: its dynamic BSDF and light-sampling routines inlined (shade -2.5 % on C4, profiles/r2_exp_shade_inline_gridconstant.log part 7)
+#endif
+#if PBRS_INLINE_DYN
+#define PB_CALL_DYN PB_DEV
+#else
+#define PB_CALL_DYN PB_CALL
+#endif
 // ---- lobes ----
 enum { LOBE_SPECULAR = 0, LOBE_LAMBERT = 1, LOBE_MICROFACET = 2 };
 enum { FR_NOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2 };
@@ -427,7 +435,7 @@ PB_DEV void bxdfs_at_t(const DeviceScene &sc, const MaterialRec &m, const Isect 
     }
 }
 
-PB_CALL void bxdfs_at_dyn(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) { bxdfs_at_t<PBRS_CLS_ANY>(sc, m, h, L, dg); }
+PB_CALL_DYN void bxdfs_at_dyn(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) { bxdfs_at_t<PBRS_CLS_ANY>(sc, m, h, L, dg); }
 template <int CLS>
 PB_DEV void bxdfs_at(const DeviceScene &sc, const MaterialRec &m, const Isect &h, Lobes &L, Diag &dg) {
     if constexpr (CLS == PBRS_CLS_ANY || CLS == PBRS_CLS_MULTI) bxdfs_at_dyn(sc, m, h, L, dg);
@@ -518,9 +526,9 @@ PB_DEV void bsdf_sample_t(const Frame &fr, const Lobes &L, vec3 wo_world, float 
     wi_out = to_world(fr, wi);
     pr = Density(overall);
 }
-PB_CALL color bsdf_eval_dyn(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) { return bsdf_eval_t<-1>(fr, L, wo_w, wi_w, dg); }
-PB_CALL float bsdf_pdf_dyn(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) { return bsdf_pdf_t<-1>(fr, L, wo_w, wi_w, dg); }
-PB_CALL void bsdf_sample_dyn(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr, Diag &dg) {
+PB_CALL_DYN color bsdf_eval_dyn(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) { return bsdf_eval_t<-1>(fr, L, wo_w, wi_w, dg); }
+PB_CALL_DYN float bsdf_pdf_dyn(const Frame &fr, const Lobes &L, vec3 wo_w, vec3 wi_w, Diag &dg) { return bsdf_pdf_t<-1>(fr, L, wo_w, wi_w, dg); }
+PB_CALL_DYN void bsdf_sample_dyn(const Frame &fr, const Lobes &L, vec3 wo_world, float u, float v, color &f, vec3 &wi_out, Prob &pr, Diag &dg) {
     bsdf_sample_t<-1>(fr, L, wo_world, u, v, f, wi_out, pr, dg);
 }
 template <int K>

@@ -355,7 +355,7 @@ PB_DEV int sample_one_light_t(const DeviceScene &sc, const Isect &hit, const Lob
     return 1;
 }
 
-PB_CALL int sample_one_light_dyn(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
+PB_CALL_DYN int sample_one_light_dyn(const DeviceScene &sc, const Isect &hit, const Lobes &L, const Frame &fr, const Sampler &smp, uint32_t base,
                                 ShadowOut &so, Diag &dg) {
     return sample_one_light_t<-1>(sc, hit, L, fr, smp, base, so, dg);
 }
